@@ -1,0 +1,73 @@
+/* oracle/rimphony_oracle.h -- TEST INFRASTRUCTURE ONLY (see rimphony_oracle.c). */
+#ifndef RIMPHONY_ORACLE_H
+#define RIMPHONY_ORACLE_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* same numbering as include/rimphony_b200.h */
+enum { ORC_DIST_POWER_LAW = 0, ORC_DIST_THERMAL_JUETTNER = 1, ORC_DIST_PITCHY_PL = 2, ORC_DIST_PITCHY_KAPPA = 3 };
+enum { ORC_COEFF_EMISSION = 0, ORC_COEFF_ABSORPTION = 1, ORC_COEFF_FARADAY = 2 };
+enum { ORC_STOKES_I = 0, ORC_STOKES_Q = 1, ORC_STOKES_V = 2 };
+
+typedef struct {
+    int kind;
+    double p, k;
+    double gamma_min, gamma_max, inv_gamma_cutoff;
+    double kappa, width, inv_kappa_width;
+    double neg_inverse_t;
+    double norm;
+} orc_dist;
+
+typedef struct {
+    uint64_t n_symphony_integrand;
+    uint64_t n_gamma_qag;
+    uint64_t n_gamma_qag_failed;
+    uint64_t n_chunks;
+    uint64_t max_gamma_intervals;
+    uint64_t max_n_intervals;
+    uint64_t n_heyvaerts_element;
+    uint64_t n_heyvaerts_qag;
+    uint64_t n_heyvaerts_jy;
+    double hey_nr_val, hey_qr_val;
+} orc_stats;
+
+int orc_dist_init(orc_dist *d, int kind, const double *params, int n_params);
+double orc_calc_f(const orc_dist *d, double gamma, double cos_xi);
+void orc_calc_f_derivatives(const orc_dist *d, double gamma, double cos_xi, double *dfdg, double *dfdcx);
+
+double orc_symphony(const orc_dist *d, int coeff, int stokes, double s, double theta, orc_stats *stats);
+double orc_symphony_lobes(const orc_dist *d, int coeff, int stokes, double s, double theta,
+                          orc_stats *stats, double lobes[2]);
+double orc_heyvaerts(const orc_dist *d, int stokes, double s, double theta, orc_stats *stats);
+
+double orc_compute_dimensionless(const orc_dist *d, int coeff, int stokes, double s, double theta,
+                                 orc_stats *stats);
+double orc_compute_cgs(const orc_dist *d, int coeff, int stokes, double nu, double b, double n_e,
+                       double theta, orc_stats *stats);
+void orc_compute_all_dimensionless(const orc_dist *d, double s, double theta, double out[8],
+                                   double lobes[4], orc_stats *stats);
+int orc_batch_compute_all_dimensionless(int kind, int64_t n_points, const double *s,
+                                        const double *theta, const double *const *params,
+                                        int n_params, unsigned coeff_mask, double *out8,
+                                        double *lobes4, int n_threads);
+int orc_num_threads(void);
+
+double orc_ref_bessel_j(double n, double x);
+double orc_ref_bessel_dj(double n, double x);
+double orc_test_bessel_i(double nu, double x);
+void orc_test_bessel_jy(double nu, double x, double *j, double *y);
+double orc_test_bessel_k2(double z);
+double orc_test_pitch_angle_integral(double k);
+int orc_test_qag(int which, double a_param, double lo, double hi, double epsrel, double *result,
+                 double *abserr, int *n_intervals);
+double orc_test_deriv(int which, double a_param, double x, double h);
+void orc_gk31_tables(double xgk[16], double wgk[16], double wg[8]);
+
+#ifdef __cplusplus
+}
+#endif
+#endif
