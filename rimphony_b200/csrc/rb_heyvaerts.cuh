@@ -1,0 +1,337 @@
+// rb_heyvaerts.cuh -- Faraday conversion (rho_Q, Heyvaerts' "h") and rotation
+// (rho_V, "f") coefficients by the Heyvaerts et al. (2013) non-resonant (NR) +
+// quasi-resonant (QR) double integrals in (sigma, pomega).
+//
+// Replaces (reference file:line):
+//   src/heyvaerts.rs:60-191    compute_dimensionless / CalculationState::compute
+//   src/heyvaerts.rs:194-201   fill_coord_vars
+//   src/heyvaerts.rs:204-296   nr/qr outer integrals and integrands
+//   src/heyvaerts.rs:302-468   h_qr, h_nr, f_qr, f_nr elements
+//   src/heyvaerts.rs:472-493   dfdsigma
+//
+// FUSED: h and f share every node (coordinates, df/dsigma, the four I_{+-1/3},
+// I_{+-2/3} or the J/Y pair) and are converged together.  !FUSED: one
+// coefficient per pass with the reference's exact sequence of rule applications.
+#pragma once
+
+#include "rb_core.cuh"
+#include "rb_dist.cuh"
+#include "rb_special.cuh"
+
+namespace rb {
+
+constexpr double kFourOverSqrt27 = 0.769800358919501;
+constexpr double kInverseC = 1.0 / kSpeedLight;
+constexpr double kInverseSqrt3 = 0.5773502691896257;
+constexpr double kSqrt8Over3 = 0.9428090415820635;
+constexpr double kThreeTwoThirds = 2.080083823051904;
+constexpr double kGApproximationCutoff = 10.0;
+constexpr int kHeyMaxSteps = 400; // safety net for the outward stepping loops
+
+struct HeyGeometry {
+    double cos_th, sin_th;
+    double sigma0, sigma0_sq;
+};
+
+// Heyvaerts coordinates of one node (heyvaerts.rs:194-201) and df/dsigma
+// (heyvaerts.rs:472-493).
+template <int KIND>
+struct HeyNode {
+    double sigma, pomega, x, dfds;
+
+    RB_FN void fill(const Dist &d, const HeyGeometry &g, double sigma_, double pomega_)
+    {
+        sigma = sigma_;
+        pomega = pomega_;
+        x = sqrt(sigma * sigma - pomega * pomega - g.sigma0_sq);
+        const double t = g.sigma0 * g.sin_th;
+        const double gamma = (sigma - pomega * g.cos_th) / t;
+        const double mu = (sigma * g.cos_th - pomega) / (t * sqrt(gamma * gamma - 1.0));
+
+        double f, dfdg, dfdcxi;
+        dist_eval<KIND>(d, gamma, mu, f, dfdg, dfdcxi);
+        const double g_term = dfdg / t;
+        double mu_term = 0.0;
+        if (dfdcxi != 0.0) {
+            const double q = sigma - pomega * g.cos_th;
+            const double r = pomega - sigma * g.cos_th;
+            const double u = q * q - t * t;
+            const double dcxi_dsigma = (q * u * g.cos_th + u * r + r * t * t) / (u * sqrt(u) * q);
+            mu_term = dcxi_dsigma * dfdcxi;
+        }
+        dfds = g_term + mu_term;
+    }
+};
+
+// NR elements (heyvaerts.rs:379-394 and 453-468); inner variable sigma.
+template <int KIND, int NV>
+struct HeyNRIntegrand {
+    const Dist *d;
+    const HeyGeometry *g;
+    double pomega;
+    int sel; // 0 = h (rho_Q), 1 = f (rho_V) when NV == 1
+
+    RB_FN void eval(double sigma, double (&out)[NV]) const
+    {
+        HeyNode<KIND> nd;
+        nd.fill(*d, *g, sigma, pomega);
+        const double s_sq = sigma * sigma;
+        const double x_sq = nd.x * nd.x;
+        const double v = s_sq - x_sq;
+        const double sv = sqrt(v);
+        const double ratio = s_sq / v;
+        const double a1 = 1.0 / 8.0 - 5.0 / 24.0 * ratio;
+        const double a2 = 3.0 / 128.0 - 77.0 / 576.0 * ratio + 385.0 / 3456.0 * (ratio * ratio);
+        const double xa1p = -5.0 / 12.0 * s_sq * x_sq / (v * v);
+        const double v15 = v * sv, v25 = v * v * sv;
+
+        const double t1 = (6.0 * a2 - a1 * a1 + xa1p) / sv + a1 * x_sq / v15 - x_sq * x_sq / v25 / 8.0;
+        const double t2 = (6.0 * a2 - a1 * a1) / v15;
+        const double u1 = 2.0 * t1 - g->sigma0_sq * t2;
+        const double h = kPi * kInverseC * u1 * nd.dfds;
+
+        const double z = 0.5 * x_sq / v15 + (6.0 * a2 + xa1p - a1 * a1) / v + 1.5 * a1 * x_sq / (v * v);
+        const double f = -2.0 * kPi * kInverseC * z * pomega * nd.dfds;
+
+        if constexpr (NV == 2) {
+            out[0] = h;
+            out[1] = f;
+        } else {
+            out[0] = sel ? f : h;
+        }
+    }
+};
+
+// QR elements (heyvaerts.rs:302-373 and 400-447); inner variable pomega.
+template <int KIND, int NV>
+struct HeyQRIntegrand {
+    const Dist *d;
+    const HeyGeometry *g;
+    double sigma;
+    int sel;
+
+    RB_FN void eval(double pomega, double (&out)[NV]) const
+    {
+        HeyNode<KIND> nd;
+        nd.fill(*d, *g, sigma, pomega);
+        const double x = nd.x;
+        const double po_sq = pomega * pomega;
+        const double smx = sigma - x;
+        const double smxox = smx / x;
+        const double gg = kSqrt8Over3 * smx * sqrt(smx) / sqrt(x);
+
+        double y_h1, y_h2, y_f;
+        if (gg < kGApproximationCutoff) {
+            double ip13, im13, ip23, im23;
+            bessel_i_thirds(gg, ip13, im13, ip23, im23);
+            y_h1 = kFourOverSqrt27 * smxox * smxox * (im23 - ip23) * (im23 + ip23);
+            y_h2 = 0.5 * kFourOverSqrt27 * smxox * (im13 - ip13) * (im13 + ip13);
+            y_f = kInverseSqrt3 * gg * (im23 - ip23) * (im13 + ip13);
+        } else {
+            double js, jsm1, ys, ysm1;
+            bessel_jy_pair(sigma, x, js, jsm1, ys, ysm1);
+            const double jvp = jsm1 - sigma * js / x;
+            const double yvp = ysm1 - sigma * ys / x;
+            y_h1 = jvp * yvp;
+            y_h2 = -js * ys;
+            y_f = -x * jvp * ys;
+        }
+
+        const double t1 = kPi * kPi * x * x * y_h1;
+        const double t2 = kPi * kPi * po_sq * y_h2;
+        const double t3 = -kPi * (2.0 * po_sq + g->sigma0_sq) / sqrt(po_sq + g->sigma0_sq);
+        const double h = kInverseC * (t1 + t2 + t3) * nd.dfds;
+        const double f = -kTwoPi * kInverseC * pomega * (kPi * y_f - 1.0) * nd.dfds;
+
+        if constexpr (NV == 2) {
+            out[0] = h;
+            out[1] = f;
+        } else {
+            out[0] = sel ? f : h;
+        }
+    }
+};
+
+// Outer integrands: an inner adaptive integral per outer node.
+template <int KIND, int NV>
+struct HeyNROuter {
+    const Dist *d;
+    const HeyGeometry *g;
+    IntervalList<NV> *ilist;
+    unsigned want;
+    int sel;
+    double epsrel;
+
+    // heyvaerts.rs:213-250
+    RB_FN void eval_collective(Warp &w, double pomega, double (&out)[NV])
+    {
+        const double sigma_min = sqrt(pomega * pomega + g->sigma0_sq);
+        const double sigma_max = kInverseSqrt3 * sigma_min * sqrt(sigma_min);
+        if (sigma_max <= sigma_min) {
+#pragma unroll
+            for (int c = 0; c < NV; c++)
+                out[c] = 0.0;
+            return;
+        }
+        HeyNRIntegrand<KIND, NV> f{d, g, pomega, sel};
+        ApplyLanes<NV, HeyNRIntegrand<KIND, NV>> ap{f};
+        const double bounds[2] = {sigma_min, sigma_max};
+        qag_joint<PolicyPlain<NV>>(w, ap, 1, bounds, epsrel, *ilist, want, out);
+    }
+};
+
+template <int KIND, int NV>
+struct HeyQROuter {
+    const Dist *d;
+    const HeyGeometry *g;
+    IntervalList<NV> *ilist;
+    unsigned want;
+    int sel;
+    double epsrel;
+
+    // heyvaerts.rs:262-296
+    RB_FN void eval_collective(Warp &w, double sigma, double (&out)[NV])
+    {
+        const double pomega_max_phys = sqrt(kThreeTwoThirds * cbrt(sigma) * sigma - g->sigma0_sq);
+        const double pomega_max_qr = sqrt(sigma * sigma - g->sigma0_sq);
+        const double pomega_max = fmin(pomega_max_phys, pomega_max_qr);
+        HeyQRIntegrand<KIND, NV> f{d, g, sigma, sel};
+        ApplyLanes<NV, HeyQRIntegrand<KIND, NV>> ap{f};
+        const double bounds[2] = {-pomega_max, pomega_max};
+        qag_joint<PolicyPlain<NV>>(w, ap, 1, bounds, epsrel, *ilist, want, out);
+    }
+};
+
+template <bool FUSED, int INNER_CAP, int OUTER_CAP>
+struct HeyWorkspace {
+    static constexpr int NV = FUSED ? 2 : 1;
+    double inner_store[INNER_CAP * IntervalList<NV>::doubles_per_interval];
+    double outer_store[OUTER_CAP * IntervalList<NV>::doubles_per_interval];
+};
+
+// One outward-stepping stage of heyvaerts.rs:102-185.
+//   dir = +1: integrate [edge, edge + delta], dir = -1: [edge - delta, edge].
+//   first_needs_value: the derivative probe and the relative-contribution test
+//   are skipped while the running value is exactly zero (NR right side, QR).
+template <int NV, bool REFINE, class Outer>
+RB_FN void hey_step_outward(Warp &w, Outer &F, IntervalList<NV> &olist, double epsrel_outer, double edge,
+                            double delta, int dir, bool skip_while_zero, double delta_cap, double (&val)[NV],
+                            unsigned &alive)
+{
+    constexpr double kTol = 1e-5, kDeltaScale = 5.0;
+    ApplySeq<NV, Outer> ap{F};
+    unsigned keep = alive;
+    int steps = 0;
+
+    while (keep) {
+        if (++steps > kHeyMaxSteps) {
+            w.status |= kStatusCapHit;
+            break;
+        }
+        F.want = keep;
+
+        unsigned voters = 0;
+#pragma unroll
+        for (int c = 0; c < NV; c++)
+            if (((keep >> c) & 1u) && !(skip_while_zero && val[c] == 0.0))
+                voters |= 1u << c;
+
+        if (voters) {
+            double rel_deriv[NV];
+            deriv_central_joint<NV, REFINE>(w, F, edge, 1e-6, rel_deriv);
+            bool grow = true;
+#pragma unroll
+            for (int c = 0; c < NV; c++) {
+                if (!((voters >> c) & 1u))
+                    continue;
+                const bool g_c = (rel_deriv[c] == 0.0) || (fabs(1.0 / (rel_deriv[c] * delta)) > kDeltaScale);
+                grow = grow && g_c;
+            }
+            if (grow && delta < delta_cap)
+                delta *= kDeltaScale;
+        }
+
+        const double bounds[2] = {dir > 0 ? edge : edge - delta, dir > 0 ? edge + delta : edge};
+        double contrib[NV];
+        qag_joint<PolicyPlain<NV>>(w, ap, 1, bounds, epsrel_outer, olist, keep, contrib);
+
+#pragma unroll
+        for (int c = 0; c < NV; c++) {
+            if (!((keep >> c) & 1u))
+                continue;
+            if (!(contrib[c] == contrib[c])) { // NaN: the reference returns NaN
+                val[c] = NAN;
+                alive &= ~(1u << c);
+                keep &= ~(1u << c);
+                continue;
+            }
+            if (!(skip_while_zero && val[c] == 0.0)) {
+                if (!(fabs(contrib[c] / val[c]) > kTol))
+                    keep &= ~(1u << c);
+            }
+            val[c] += contrib[c];
+        }
+        edge += dir * delta;
+    }
+}
+
+// rho_Q and rho_V of one point, dimensionless (heyvaerts.rs:60-191).
+template <int KIND, bool FUSED, int INNER_CAP, int OUTER_CAP>
+RB_FN void heyvaerts_point(Warp &w, const Dist &dist, double s, double theta, double epsrel_inner,
+                           double epsrel_outer, HeyWorkspace<FUSED, INNER_CAP, OUTER_CAP> &ws, double (&out2)[2])
+{
+    constexpr int NV = FUSED ? 2 : 1;
+    HeyGeometry geom;
+    geom.cos_th = cos(theta);
+    geom.sin_th = sin(theta);
+    geom.sigma0 = s * geom.sin_th;
+    geom.sigma0_sq = geom.sigma0 * geom.sigma0;
+
+    IntervalList<NV> ilist, olist;
+    ilist.bind(ws.inner_store, INNER_CAP);
+    olist.bind(ws.outer_store, OUTER_CAP);
+
+    const unsigned all = FUSED ? 3u : 1u;
+    const double scale = 2.0 * kElectronCharge * kElectronCharge /
+                         (kMassElectron * (s * geom.sin_th) * (s * geom.sin_th));
+
+    constexpr int n_pass = FUSED ? 1 : 2;
+    for (int pass = 0; pass < n_pass; pass++) {
+        HeyNROuter<KIND, NV> nr{&dist, &geom, &ilist, all, pass, epsrel_inner};
+        HeyQROuter<KIND, NV> qr{&dist, &geom, &ilist, all, pass, epsrel_inner};
+        unsigned alive = all;
+
+        // initial NR integral over [-3 sigma0, 3 sigma0]
+        double nr_val[NV];
+        {
+            ApplySeq<NV, HeyNROuter<KIND, NV>> ap{nr};
+            const double bounds[2] = {-3.0 * geom.sigma0, 3.0 * geom.sigma0};
+            qag_joint<PolicyPlain<NV>>(w, ap, 1, bounds, epsrel_outer, olist, all, nr_val);
+#pragma unroll
+            for (int c = 0; c < NV; c++)
+                if (!(nr_val[c] == nr_val[c]))
+                    alive &= ~(1u << c);
+        }
+
+        const double p3 = 3.0 * geom.sigma0;
+        hey_step_outward<NV, !FUSED>(w, nr, olist, epsrel_outer, p3, p3, +1, true, INFINITY, nr_val, alive);
+        hey_step_outward<NV, !FUSED>(w, nr, olist, epsrel_outer, -p3, p3, -1, false, INFINITY, nr_val, alive);
+
+        double qr_val[NV];
+#pragma unroll
+        for (int c = 0; c < NV; c++)
+            qr_val[c] = 0.0;
+        const double s15 = kInverseSqrt3 * geom.sigma0 * sqrt(geom.sigma0);
+        const double sigma_low = geom.sigma0 > s15 ? geom.sigma0 : s15;
+        hey_step_outward<NV, !FUSED>(w, qr, olist, epsrel_outer, sigma_low, geom.sigma0, +1, true,
+                                     1e6 * geom.sigma0, qr_val, alive);
+
+#pragma unroll
+        for (int c = 0; c < NV; c++) {
+            const double v = ((alive >> c) & 1u) ? scale * (nr_val[c] + qr_val[c]) : NAN;
+            out2[FUSED ? c : pass] = v;
+        }
+    }
+}
+
+} // namespace rb

@@ -1,0 +1,926 @@
+// rimphony_b200.cu -- sm_100a kernels and the C ABI (include/rimphony_b200.h).
+//
+// Three persistent, warp-per-point kernels per distribution kind:
+//   k_normalize   full_calculation(): the normalisation constant of each point
+//   k_symphony    j_I, alpha_I, j_Q, alpha_Q, j_V, alpha_V       (rb_symphony.cuh)
+//   k_heyvaerts   rho_Q, rho_V                                    (rb_heyvaerts.cuh)
+// Points are independent, their cost varies by more than 10x, so each warp
+// pulls the next point from a global atomic counter.  All arithmetic is FP64 on
+// the CUDA cores; there is no dense contraction for the tensor cores to do.
+//
+// There is deliberately no host implementation behind these entry points: with
+// no usable CUDA device every call fails with a nonzero return code.
+#include <cuda_runtime.h>
+
+#include <atomic>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <mutex>
+#include <string>
+#include <thread>
+#include <vector>
+
+#include "../../include/rimphony_b200.h"
+#include "rb_heyvaerts.cuh"
+#include "rb_symphony.cuh"
+
+namespace {
+
+using namespace rb;
+
+// ---------------------------------------------------------------------------
+// launch geometry
+
+constexpr int kWarpsPerBlock = 4;
+constexpr int kThreadsPerBlock = kWarpsPerBlock * 32;
+
+constexpr int kSymGammaCap = 48; // observed high-water mark 36
+constexpr int kSymNCap = 48;
+constexpr int kHeyInnerCap = 128; // observed 112 in the s sin(theta) < 3 corner
+constexpr int kHeyOuterCap = 64;
+constexpr int kNormCap = 128; // QAG to 1e-8 on [1, 1e12] needs ~40 live intervals
+
+constexpr int kMaxParams = 8;
+
+struct BatchArgs {
+    long long n;
+    const double *s;
+    const double *theta;
+    const double *params[kMaxParams];
+    int n_params;
+    unsigned bcast;
+    double *norm;
+    double *out8;
+    double *lobes4;
+    int *status;
+    unsigned *counters;
+    unsigned long long *next;
+    unsigned coeff_mask;
+    double eps_gamma, eps_n, eps_hey_inner, eps_hey_outer;
+    double sigma0_lo, sigma0_hi; // Heyvaerts: only points with sigma0 in [lo, hi)
+};
+
+__device__ __forceinline__ long long next_point(unsigned long long *counter, int lane)
+{
+    unsigned long long i = 0;
+    if (lane == 0)
+        i = atomicAdd(counter, 1ULL);
+    return (long long)__shfl_sync(0xffffffffu, i, 0);
+}
+
+template <int KIND>
+__device__ __forceinline__ bool load_dist(const BatchArgs &a, long long i, Dist &d, double &first_param)
+{
+    double pv[kMaxParams];
+#pragma unroll
+    for (int j = 0; j < kMaxParams; j++)
+        pv[j] = (j < a.n_params) ? a.params[j][((a.bcast >> j) & 1u) ? 0 : i] : 0.0;
+    first_param = pv[0];
+    return dist_from_params<KIND>(pv, a.n_params, d);
+}
+
+// ---------------------------------------------------------------------------
+// kernels
+
+template <int KIND>
+__global__ void __launch_bounds__(kThreadsPerBlock) k_normalize(BatchArgs a)
+{
+    extern __shared__ double smem[];
+    const int warp = threadIdx.x >> 5;
+    double *store = smem + (size_t)warp * kNormCap * IntervalList<1>::doubles_per_interval;
+    Warp w;
+    w.init();
+    const long long stride = (long long)gridDim.x * kWarpsPerBlock;
+    for (long long i = (long long)blockIdx.x * kWarpsPerBlock + warp; i < a.n; i += stride) {
+        w.status = 0;
+        Dist d;
+        double p0;
+        bool ok = load_dist<KIND>(a, i, d, p0);
+        if (ok) {
+            IntervalList<1> list;
+            list.bind(store, kNormCap);
+            ok = dist_normalize<KIND>(w, d, p0, list);
+        }
+        if (w.lane == 0) {
+            a.norm[i] = ok ? d.norm : NAN;
+            if (a.status && (!ok || w.status))
+                atomicOr(&a.status[i], (int)(w.status | (ok ? 0u : kStatusNormFailed)));
+        }
+    }
+}
+
+template <int KIND, bool FUSED>
+__global__ void __launch_bounds__(kThreadsPerBlock, FUSED ? 3 : 4) k_symphony(BatchArgs a)
+{
+    using WS = SymWorkspace<FUSED, kSymGammaCap, kSymNCap>;
+    extern __shared__ double smem[];
+    const int warp = threadIdx.x >> 5;
+    WS &ws = reinterpret_cast<WS *>(smem)[warp];
+    Warp w;
+    w.init();
+
+    for (;;) {
+        const long long i = next_point(a.next, w.lane);
+        if (i >= a.n)
+            break;
+        w.status = 0;
+        w.n_apply_lanes = 0;
+
+        Dist d;
+        double p0;
+        load_dist<KIND>(a, i, d, p0);
+        d.norm = a.norm[i];
+
+        double out6[6], lobes4[4];
+        symphony_point<KIND, FUSED, kSymGammaCap, kSymNCap>(w, d, a.s[i], a.theta[i], a.eps_gamma, a.eps_n, ws, out6,
+                                                            lobes4);
+
+        if (w.lane == 0) {
+            bool any_nan = false;
+#pragma unroll
+            for (int c = 0; c < 6; c++) {
+                if ((a.coeff_mask >> c) & 1u) {
+                    a.out8[(long long)c * a.n + i] = out6[c];
+                    any_nan |= !(out6[c] == out6[c]);
+                }
+            }
+            if (a.lobes4) {
+#pragma unroll
+                for (int c = 0; c < 4; c++)
+                    a.lobes4[(long long)c * a.n + i] = lobes4[c];
+            }
+            if (a.counters)
+                a.counters[i] = w.n_apply_lanes;
+            const unsigned st = w.status | (any_nan ? kStatusNaN : 0u);
+            if (a.status && st)
+                atomicOr(&a.status[i], (int)st);
+        }
+    }
+}
+
+template <int KIND, bool FUSED>
+__global__ void __launch_bounds__(kThreadsPerBlock, 4) k_heyvaerts(BatchArgs a)
+{
+    using WS = HeyWorkspace<FUSED, kHeyInnerCap, kHeyOuterCap>;
+    extern __shared__ double smem[];
+    const int warp = threadIdx.x >> 5;
+    WS &ws = reinterpret_cast<WS *>(smem)[warp];
+    Warp w;
+    w.init();
+
+    for (;;) {
+        const long long i = next_point(a.next, w.lane);
+        if (i >= a.n)
+            break;
+        const double s = a.s[i], theta = a.theta[i];
+        const double sigma0 = s * sin(theta);
+        if (!(sigma0 >= a.sigma0_lo && sigma0 < a.sigma0_hi) && !(a.sigma0_lo < 0.0 && !(sigma0 == sigma0)))
+            continue; // another launch owns this point (NaN sigma0 goes with the lowest band)
+        w.status = 0;
+        w.n_apply_lanes = 0;
+
+        Dist d;
+        double p0;
+        load_dist<KIND>(a, i, d, p0);
+        d.norm = a.norm[i];
+
+        double out2[2];
+        heyvaerts_point<KIND, FUSED, kHeyInnerCap, kHeyOuterCap>(w, d, s, theta, a.eps_hey_inner, a.eps_hey_outer, ws,
+                                                                 out2);
+
+        if (w.lane == 0) {
+            bool any_nan = false;
+#pragma unroll
+            for (int c = 0; c < 2; c++) {
+                if ((a.coeff_mask >> (6 + c)) & 1u) {
+                    a.out8[(long long)(6 + c) * a.n + i] = out2[c];
+                    any_nan |= !(out2[c] == out2[c]);
+                }
+            }
+            if (a.counters)
+                a.counters[a.n + i] = w.n_apply_lanes;
+            const unsigned st = w.status | (any_nan ? kStatusNaN : 0u);
+            if (a.status && st)
+                atomicOr(&a.status[i], (int)st);
+        }
+    }
+}
+
+// test entry points: the device Bessel evaluator and the distribution functions
+__global__ void k_bessel(long long count, const double *n, const double *x, double *j, double *dj)
+{
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= count)
+        return;
+    LeungOrder o, o1;
+    leung_prepare(n[i], o);
+    leung_prepare(n[i] + 1.0, o1);
+    double jn, djn;
+    leung_j_and_dj(o, o1, x[i], jn, djn);
+    j[i] = jn;
+    dj[i] = djn;
+}
+
+template <int KIND>
+__global__ void k_dist_eval(Dist d, long long count, const double *gamma, const double *cos_xi, double *out3)
+{
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= count)
+        return;
+    double f, a, b;
+    dist_eval<KIND>(d, gamma[i], cos_xi[i], f, a, b);
+    out3[i] = f;
+    out3[count + i] = a;
+    out3[2 * count + i] = b;
+}
+
+// ---------------------------------------------------------------------------
+// host side
+
+thread_local std::string g_error;
+std::atomic<uint64_t> g_launches{0};
+
+int fail(const char *fmt, ...)
+{
+    char buf[512];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof buf, fmt, ap);
+    va_end(ap);
+    g_error = buf;
+    return 1;
+}
+
+#define RB_CUDA(call)                                                                              \
+    do {                                                                                           \
+        cudaError_t e_ = (call);                                                                   \
+        if (e_ != cudaSuccess)                                                                     \
+            return fail("%s failed: %s (%s:%d)", #call, cudaGetErrorString(e_), __FILE__, __LINE__); \
+    } while (0)
+
+struct DeviceBuffer {
+    void *ptr = nullptr;
+    size_t bytes = 0;
+    int reserve(size_t want)
+    {
+        if (want <= bytes)
+            return 0;
+        if (ptr)
+            cudaFree(ptr);
+        ptr = nullptr;
+        bytes = 0;
+        cudaError_t e = cudaMalloc(&ptr, want);
+        if (e != cudaSuccess)
+            return fail("cudaMalloc(%zu) failed: %s", want, cudaGetErrorString(e));
+        bytes = want;
+        return 0;
+    }
+    void release()
+    {
+        if (ptr)
+            cudaFree(ptr);
+        ptr = nullptr;
+        bytes = 0;
+    }
+};
+
+struct DeviceContext {
+    bool ready = false;
+    int device = -1;
+    int sm_count = 0;
+    cudaStream_t stream = nullptr;       // Symphony + copies
+    cudaStream_t stream_hey = nullptr;   // Heyvaerts, overlaps the Symphony tail
+    cudaEvent_t ev[8] = {};
+    DeviceBuffer in, out, scratch, counters;
+    float last_ms[4] = {0, 0, 0, 0};
+    std::mutex lock;
+};
+
+constexpr int kMaxDevices = 16;
+DeviceContext g_ctx[kMaxDevices];
+std::mutex g_ctx_lock;
+
+int get_context(int device, DeviceContext **out)
+{
+    if (device < 0)
+        RB_CUDA(cudaGetDevice(&device));
+    if (device >= kMaxDevices)
+        return fail("device ordinal %d out of range", device);
+    DeviceContext &c = g_ctx[device];
+    std::lock_guard<std::mutex> g(g_ctx_lock);
+    if (!c.ready) {
+        int count = 0;
+        RB_CUDA(cudaGetDeviceCount(&count));
+        if (device >= count)
+            return fail("CUDA device %d not present (%d visible)", device, count);
+        RB_CUDA(cudaSetDevice(device));
+        cudaDeviceProp prop;
+        RB_CUDA(cudaGetDeviceProperties(&prop, device));
+        c.sm_count = prop.multiProcessorCount;
+        RB_CUDA(cudaStreamCreateWithFlags(&c.stream, cudaStreamNonBlocking));
+        RB_CUDA(cudaStreamCreateWithFlags(&c.stream_hey, cudaStreamNonBlocking));
+        for (auto &e : c.ev)
+            RB_CUDA(cudaEventCreate(&e));
+        c.device = device;
+        c.ready = true;
+    }
+    *out = &c;
+    return 0;
+}
+
+struct ResolvedOptions {
+    int mode;
+    unsigned coeff_mask;
+    unsigned bcast;
+    int device;
+    double eps_gamma, eps_n, eps_hi, eps_ho;
+};
+
+ResolvedOptions resolve(const rimphony_b200_options *o)
+{
+    ResolvedOptions r{RIMPHONY_B200_MODE_FUSED, 0xFFu, 0u, -1, 1e-3, 1e-3, 1e-3, 1e-3};
+    if (!o)
+        return r;
+    rimphony_b200_options tmp;
+    memset(&tmp, 0, sizeof tmp);
+    const size_t sz = o->struct_size ? (o->struct_size < sizeof tmp ? o->struct_size : sizeof tmp) : sizeof tmp;
+    memcpy(&tmp, o, sz);
+    r.mode = tmp.mode;
+    r.coeff_mask = tmp.coeff_mask ? (tmp.coeff_mask & 0xFFu) : 0xFFu;
+    r.bcast = tmp.param_broadcast_mask;
+    r.device = tmp.device;
+    if (tmp.epsrel_gamma > 0)
+        r.eps_gamma = tmp.epsrel_gamma;
+    if (tmp.epsrel_n > 0)
+        r.eps_n = tmp.epsrel_n;
+    if (tmp.epsrel_heyvaerts_inner > 0)
+        r.eps_hi = tmp.epsrel_heyvaerts_inner;
+    if (tmp.epsrel_heyvaerts_outer > 0)
+        r.eps_ho = tmp.epsrel_heyvaerts_outer;
+    return r;
+}
+
+int check_params(int kind, int n_params)
+{
+    switch (kind) {
+    case RIMPHONY_B200_POWER_LAW:
+        return (n_params == 1 || n_params == 4) ? 0 : fail("POWER_LAW takes 1 or 4 parameter columns, got %d", n_params);
+    case RIMPHONY_B200_THERMAL_JUETTNER:
+        return n_params == 1 ? 0 : fail("THERMAL_JUETTNER takes 1 parameter column, got %d", n_params);
+    case RIMPHONY_B200_PITCHY_PL:
+        return (n_params == 2 || n_params == 5) ? 0 : fail("PITCHY_PL takes 2 or 5 parameter columns, got %d", n_params);
+    case RIMPHONY_B200_PITCHY_KAPPA:
+        return (n_params == 3 || n_params == 4) ? 0 : fail("PITCHY_KAPPA takes 3 or 4 parameter columns, got %d", n_params);
+    }
+    return fail("unknown distribution kind %d", kind);
+}
+
+template <class K>
+int set_smem(K kernel, size_t bytes)
+{
+    RB_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
+    return 0;
+}
+
+template <class K>
+int persistent_grid(K kernel, size_t smem, int sm_count, int *grid)
+{
+    int per_sm = 0;
+    RB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, kThreadsPerBlock, smem));
+    if (per_sm < 1)
+        return fail("kernel does not fit on an SM (smem %zu)", smem);
+    *grid = per_sm * sm_count; // one resident CTA slot each, a multiple of the SM count
+    return 0;
+}
+
+template <int KIND>
+int launch_kind(DeviceContext &c, BatchArgs a, const ResolvedOptions &o, cudaStream_t user_stream)
+{
+    cudaStream_t st = user_stream ? user_stream : c.stream;
+    cudaStream_t st_hey = user_stream ? user_stream : c.stream_hey;
+    unsigned long long *counters = static_cast<unsigned long long *>(c.counters.ptr);
+    const bool faithful = (o.mode == RIMPHONY_B200_MODE_FAITHFUL);
+    const bool want_sym = (o.coeff_mask & 0x3Fu) != 0;
+    const bool want_hey = (o.coeff_mask & 0xC0u) != 0;
+
+    RB_CUDA(cudaMemsetAsync(counters, 0, 4 * sizeof(unsigned long long), st));
+    RB_CUDA(cudaEventRecord(c.ev[0], st));
+
+    // 1. normalisation
+    {
+        const size_t smem = (size_t)kWarpsPerBlock * kNormCap * IntervalList<1>::doubles_per_interval * sizeof(double);
+        int grid = 0;
+        if (set_smem(k_normalize<KIND>, smem) || persistent_grid(k_normalize<KIND>, smem, c.sm_count, &grid))
+            return 1;
+        const long long need = (a.n + kWarpsPerBlock - 1) / kWarpsPerBlock;
+        if (need < grid)
+            grid = (int)need;
+        k_normalize<KIND><<<grid, kThreadsPerBlock, smem, st>>>(a);
+        g_launches++;
+        RB_CUDA(cudaGetLastError());
+    }
+    RB_CUDA(cudaEventRecord(c.ev[1], st));
+    if (st_hey != st)
+        RB_CUDA(cudaStreamWaitEvent(st_hey, c.ev[1], 0));
+
+    // 2. Symphony
+    if (want_sym) {
+        a.next = counters + 0;
+        int grid = 0;
+        if (faithful) {
+            const size_t smem = kWarpsPerBlock * sizeof(SymWorkspace<false, kSymGammaCap, kSymNCap>);
+            if (set_smem(k_symphony<KIND, false>, smem) || persistent_grid(k_symphony<KIND, false>, smem, c.sm_count, &grid))
+                return 1;
+            k_symphony<KIND, false><<<grid, kThreadsPerBlock, smem, st>>>(a);
+        } else {
+            const size_t smem = kWarpsPerBlock * sizeof(SymWorkspace<true, kSymGammaCap, kSymNCap>);
+            if (set_smem(k_symphony<KIND, true>, smem) || persistent_grid(k_symphony<KIND, true>, smem, c.sm_count, &grid))
+                return 1;
+            k_symphony<KIND, true><<<grid, kThreadsPerBlock, smem, st>>>(a);
+        }
+        g_launches++;
+        RB_CUDA(cudaGetLastError());
+    }
+    RB_CUDA(cudaEventRecord(c.ev[2], st));
+
+    // 3. Heyvaerts
+    RB_CUDA(cudaEventRecord(c.ev[3], st_hey));
+    if (want_hey) {
+        const double split = (o.mode == RIMPHONY_B200_MODE_FUSED) ? 3.0 : (faithful ? INFINITY : -INFINITY);
+        if (split > -INFINITY) { // faithful sequence for sigma0 < split
+            BatchArgs b = a;
+            b.next = counters + 1;
+            b.sigma0_lo = -INFINITY;
+            b.sigma0_hi = split;
+            const size_t smem = kWarpsPerBlock * sizeof(HeyWorkspace<false, kHeyInnerCap, kHeyOuterCap>);
+            int grid = 0;
+            if (set_smem(k_heyvaerts<KIND, false>, smem) || persistent_grid(k_heyvaerts<KIND, false>, smem, c.sm_count, &grid))
+                return 1;
+            k_heyvaerts<KIND, false><<<grid, kThreadsPerBlock, smem, st_hey>>>(b);
+            g_launches++;
+            RB_CUDA(cudaGetLastError());
+        }
+        if (split < INFINITY) { // fused for sigma0 >= split
+            BatchArgs b = a;
+            b.next = counters + 2;
+            b.sigma0_lo = split;
+            b.sigma0_hi = INFINITY;
+            const size_t smem = kWarpsPerBlock * sizeof(HeyWorkspace<true, kHeyInnerCap, kHeyOuterCap>);
+            int grid = 0;
+            if (set_smem(k_heyvaerts<KIND, true>, smem) || persistent_grid(k_heyvaerts<KIND, true>, smem, c.sm_count, &grid))
+                return 1;
+            k_heyvaerts<KIND, true><<<grid, kThreadsPerBlock, smem, st_hey>>>(b);
+            g_launches++;
+            RB_CUDA(cudaGetLastError());
+        }
+    }
+    RB_CUDA(cudaEventRecord(c.ev[4], st_hey));
+    if (st_hey != st)
+        RB_CUDA(cudaStreamWaitEvent(st, c.ev[4], 0));
+    RB_CUDA(cudaEventRecord(c.ev[5], st));
+    return 0;
+}
+
+int launch(DeviceContext &c, int kind, const BatchArgs &a, const ResolvedOptions &o, cudaStream_t user_stream)
+{
+    switch (kind) {
+    case RIMPHONY_B200_POWER_LAW:
+        return launch_kind<kDistPowerLaw>(c, a, o, user_stream);
+    case RIMPHONY_B200_THERMAL_JUETTNER:
+        return launch_kind<kDistThermalJuettner>(c, a, o, user_stream);
+    case RIMPHONY_B200_PITCHY_PL:
+        return launch_kind<kDistPitchyPL>(c, a, o, user_stream);
+    case RIMPHONY_B200_PITCHY_KAPPA:
+        return launch_kind<kDistPitchyKappa>(c, a, o, user_stream);
+    }
+    return fail("unknown distribution kind %d", kind);
+}
+
+int collect_times(DeviceContext &c)
+{
+    float t;
+    RB_CUDA(cudaEventElapsedTime(&t, c.ev[0], c.ev[1]));
+    c.last_ms[0] = t;
+    RB_CUDA(cudaEventElapsedTime(&t, c.ev[1], c.ev[2]));
+    c.last_ms[1] = t;
+    RB_CUDA(cudaEventElapsedTime(&t, c.ev[3], c.ev[4]));
+    c.last_ms[2] = t;
+    RB_CUDA(cudaEventElapsedTime(&t, c.ev[0], c.ev[5]));
+    c.last_ms[3] = t;
+    return 0;
+}
+
+// Device-pointer path shared by every public entry point.
+int run_device(int kind, int64_t n, const double *s, const double *theta, const double *const *params, int n_params,
+               const ResolvedOptions &o, double *out8, int32_t *status, const rimphony_b200_extras *extras,
+               void *stream, int synchronize, DeviceContext &c)
+{
+    RB_CUDA(cudaSetDevice(c.device));
+    const size_t norm_bytes = (size_t)n * sizeof(double);
+    double *norm = extras ? extras->norm : nullptr;
+    if (!norm) {
+        if (c.scratch.reserve(norm_bytes))
+            return 1;
+        norm = static_cast<double *>(c.scratch.ptr);
+    }
+    if (c.counters.reserve(4 * sizeof(unsigned long long)))
+        return 1;
+
+    BatchArgs a;
+    memset(&a, 0, sizeof a);
+    a.n = n;
+    a.s = s;
+    a.theta = theta;
+    for (int j = 0; j < n_params; j++)
+        a.params[j] = params[j];
+    a.n_params = n_params;
+    a.bcast = o.bcast;
+    a.norm = norm;
+    a.out8 = out8;
+    a.lobes4 = extras ? extras->lobes4 : nullptr;
+    a.status = status;
+    a.counters = extras ? extras->counters : nullptr;
+    a.coeff_mask = o.coeff_mask;
+    a.eps_gamma = o.eps_gamma;
+    a.eps_n = o.eps_n;
+    a.eps_hey_inner = o.eps_hi;
+    a.eps_hey_outer = o.eps_ho;
+    a.sigma0_lo = -INFINITY;
+    a.sigma0_hi = INFINITY;
+
+    cudaStream_t user = static_cast<cudaStream_t>(stream);
+    cudaStream_t st = user ? user : c.stream;
+    if (status)
+        RB_CUDA(cudaMemsetAsync(status, 0, (size_t)n * sizeof(int32_t), st));
+    if (launch(c, kind, a, o, user))
+        return 1;
+    if (synchronize) {
+        RB_CUDA(cudaStreamSynchronize(st));
+        if (collect_times(c))
+            return 1;
+    }
+    return 0;
+}
+
+int run_host(int kind, int64_t n, const double *s, const double *theta, const double *const *params, int n_params,
+             const rimphony_b200_options *opts, double *out8, int32_t *status, const rimphony_b200_extras *extras,
+             int device_override)
+{
+    if (n < 0)
+        return fail("n_points is negative");
+    if (check_params(kind, n_params))
+        return 1;
+    if (n == 0)
+        return 0;
+    if (!s || !theta || !params || !out8)
+        return fail("null array pointer");
+    ResolvedOptions o = resolve(opts);
+    if (o.mode < 0 || o.mode > 2)
+        return fail("unknown mode %d", o.mode);
+    if (device_override >= 0)
+        o.device = device_override;
+
+    DeviceContext *cp = nullptr;
+    if (get_context(o.device, &cp))
+        return 1;
+    DeviceContext &c = *cp;
+    std::lock_guard<std::mutex> guard(c.lock);
+    RB_CUDA(cudaSetDevice(c.device));
+
+    // device staging: [s | theta | param columns] in, [out8 | status | lobes | counters | norm] out
+    size_t in_doubles = 2 * (size_t)n;
+    for (int j = 0; j < n_params; j++)
+        in_doubles += ((o.bcast >> j) & 1u) ? 1 : (size_t)n;
+    if (c.in.reserve(in_doubles * sizeof(double)))
+        return 1;
+    const bool want_lobes = extras && extras->lobes4;
+    const bool want_counters = extras && extras->counters;
+    const bool want_norm = extras && extras->norm;
+    size_t out_bytes = 8 * (size_t)n * sizeof(double) + (size_t)n * sizeof(int32_t) + 64;
+    out_bytes += want_lobes ? 4 * (size_t)n * sizeof(double) : 0;
+    out_bytes += want_counters ? 2 * (size_t)n * sizeof(uint32_t) + 64 : 0;
+    out_bytes += (size_t)n * sizeof(double);
+    if (c.out.reserve(out_bytes))
+        return 1;
+
+    double *d_in = static_cast<double *>(c.in.ptr);
+    double *d_s = d_in;
+    double *d_theta = d_in + n;
+    const double *d_params[kMaxParams] = {};
+    {
+        double *cur = d_in + 2 * n;
+        RB_CUDA(cudaMemcpyAsync(d_s, s, (size_t)n * sizeof(double), cudaMemcpyHostToDevice, c.stream));
+        RB_CUDA(cudaMemcpyAsync(d_theta, theta, (size_t)n * sizeof(double), cudaMemcpyHostToDevice, c.stream));
+        for (int j = 0; j < n_params; j++) {
+            if (!params[j])
+                return fail("params[%d] is null", j);
+            const size_t cnt = ((o.bcast >> j) & 1u) ? 1 : (size_t)n;
+            RB_CUDA(cudaMemcpyAsync(cur, params[j], cnt * sizeof(double), cudaMemcpyHostToDevice, c.stream));
+            d_params[j] = cur;
+            cur += cnt;
+        }
+    }
+
+    char *d_out = static_cast<char *>(c.out.ptr);
+    double *d_out8 = reinterpret_cast<double *>(d_out);
+    d_out += 8 * (size_t)n * sizeof(double);
+    double *d_norm = reinterpret_cast<double *>(d_out);
+    d_out += (size_t)n * sizeof(double);
+    double *d_lobes = nullptr;
+    if (want_lobes) {
+        d_lobes = reinterpret_cast<double *>(d_out);
+        d_out += 4 * (size_t)n * sizeof(double);
+    }
+    int32_t *d_status = reinterpret_cast<int32_t *>(d_out);
+    d_out += ((size_t)n * sizeof(int32_t) + 63) / 64 * 64;
+    uint32_t *d_counters = nullptr;
+    if (want_counters) {
+        d_counters = reinterpret_cast<uint32_t *>(d_out);
+        RB_CUDA(cudaMemsetAsync(d_counters, 0, 2 * (size_t)n * sizeof(uint32_t), c.stream));
+    }
+
+    // slots that are not requested come back as NaN
+    RB_CUDA(cudaMemsetAsync(d_out8, 0xFF, 8 * (size_t)n * sizeof(double), c.stream));
+
+    rimphony_b200_extras dev_extras;
+    dev_extras.lobes4 = d_lobes;
+    dev_extras.counters = d_counters;
+    dev_extras.norm = d_norm;
+    if (run_device(kind, n, d_s, d_theta, d_params, n_params, o, d_out8, d_status, &dev_extras, nullptr, 0, c))
+        return 1;
+
+    RB_CUDA(cudaMemcpyAsync(out8, d_out8, 8 * (size_t)n * sizeof(double), cudaMemcpyDeviceToHost, c.stream));
+    if (status)
+        RB_CUDA(cudaMemcpyAsync(status, d_status, (size_t)n * sizeof(int32_t), cudaMemcpyDeviceToHost, c.stream));
+    if (want_lobes)
+        RB_CUDA(cudaMemcpyAsync(extras->lobes4, d_lobes, 4 * (size_t)n * sizeof(double), cudaMemcpyDeviceToHost, c.stream));
+    if (want_counters)
+        RB_CUDA(cudaMemcpyAsync(extras->counters, d_counters, 2 * (size_t)n * sizeof(uint32_t), cudaMemcpyDeviceToHost,
+                                c.stream));
+    if (want_norm)
+        RB_CUDA(cudaMemcpyAsync(extras->norm, d_norm, (size_t)n * sizeof(double), cudaMemcpyDeviceToHost, c.stream));
+    RB_CUDA(cudaStreamSynchronize(c.stream));
+    return collect_times(c);
+}
+
+} // namespace
+
+// ---------------------------------------------------------------------------
+// C ABI
+
+extern "C" {
+
+int rimphony_b200_compute_all_dimensionless(int kind, int64_t n_points, const double *s, const double *theta,
+                                            const double *const *params, int n_params,
+                                            const rimphony_b200_options *opts, double *out8, int32_t *status)
+{
+    return run_host(kind, n_points, s, theta, params, n_params, opts, out8, status, nullptr, -1);
+}
+
+int rimphony_b200_compute_all_dimensionless_ex(int kind, int64_t n_points, const double *s, const double *theta,
+                                               const double *const *params, int n_params,
+                                               const rimphony_b200_options *opts, double *out8, int32_t *status,
+                                               const rimphony_b200_extras *extras)
+{
+    return run_host(kind, n_points, s, theta, params, n_params, opts, out8, status, extras, -1);
+}
+
+int rimphony_b200_compute_all_dimensionless_device(int kind, int64_t n_points, const double *s, const double *theta,
+                                                   const double *const *params, int n_params,
+                                                   const rimphony_b200_options *opts, double *out8, int32_t *status,
+                                                   const rimphony_b200_extras *extras, void *stream, int synchronize)
+{
+    if (n_points < 0)
+        return fail("n_points is negative");
+    if (check_params(kind, n_params))
+        return 1;
+    if (n_points == 0)
+        return 0;
+    if (!s || !theta || !params || !out8)
+        return fail("null array pointer");
+    ResolvedOptions o = resolve(opts);
+    if (o.mode < 0 || o.mode > 2)
+        return fail("unknown mode %d", o.mode);
+    DeviceContext *cp = nullptr;
+    if (get_context(o.device, &cp))
+        return 1;
+    std::lock_guard<std::mutex> guard(cp->lock);
+    return run_device(kind, n_points, s, theta, params, n_params, o, out8, status, extras, stream, synchronize, *cp);
+}
+
+int rimphony_b200_compute_all_dimensionless_multi(int kind, int64_t n_points, const double *s, const double *theta,
+                                                  const double *const *params, int n_params,
+                                                  const rimphony_b200_options *opts, double *out8, int32_t *status,
+                                                  int n_devices)
+{
+    if (n_points < 0)
+        return fail("n_points is negative");
+    if (check_params(kind, n_params))
+        return 1;
+    int visible = 0;
+    RB_CUDA(cudaGetDeviceCount(&visible));
+    if (visible < 1)
+        return fail("no CUDA device visible");
+    if (n_devices <= 0 || n_devices > visible)
+        n_devices = visible;
+    if (n_points == 0)
+        return 0;
+    const ResolvedOptions o = resolve(opts);
+
+    // Contiguous slices; out8 is slot-major over the WHOLE batch, so each shard
+    // computes into a private [8][m] block that is scattered afterwards.
+    std::vector<std::thread> workers;
+    std::vector<int> rc(n_devices, 0);
+    std::vector<std::string> msg(n_devices);
+    for (int d = 0; d < n_devices; d++) {
+        const int64_t lo = n_points * d / n_devices, hi = n_points * (d + 1) / n_devices;
+        workers.emplace_back([&, d, lo, hi]() {
+            const int64_t m = hi - lo;
+            if (m == 0)
+                return;
+            std::vector<const double *> cols(n_params);
+            for (int j = 0; j < n_params; j++)
+                cols[j] = ((o.bcast >> j) & 1u) ? params[j] : params[j] + lo;
+            std::vector<double> block(8 * (size_t)m);
+            rc[d] = run_host(kind, m, s + lo, theta + lo, cols.data(), n_params, opts, block.data(),
+                             status ? status + lo : nullptr, nullptr, d);
+            if (rc[d]) {
+                msg[d] = g_error;
+                return;
+            }
+            for (int c = 0; c < 8; c++)
+                memcpy(out8 + (size_t)c * n_points + lo, block.data() + (size_t)c * m, (size_t)m * sizeof(double));
+        });
+    }
+    for (auto &t : workers)
+        t.join();
+    for (int d = 0; d < n_devices; d++)
+        if (rc[d])
+            return fail("device %d: %s", d, msg[d].c_str());
+    return 0;
+}
+
+int rimphony_b200_compute_dimensionless(int kind, const double *params, int n_params, int coeff, int stokes, double s,
+                                        double theta, double *out)
+{
+    if (!out || !params)
+        return fail("null pointer");
+    if (coeff < 0 || coeff > 2 || stokes < 0 || stokes > 2)
+        return fail("bad coefficient/stokes selector");
+    if (check_params(kind, n_params))
+        return 1;
+    if (coeff == RIMPHONY_B200_FARADAY && stokes == RIMPHONY_B200_STOKES_I) {
+        *out = NAN; // src/lib.rs:239-240
+        return 0;
+    }
+    const int slot = (coeff == RIMPHONY_B200_FARADAY) ? (stokes == RIMPHONY_B200_STOKES_Q ? 6 : 7) : (2 * stokes + coeff);
+    rimphony_b200_options o;
+    memset(&o, 0, sizeof o);
+    o.struct_size = sizeof o;
+    o.coeff_mask = 1u << slot;
+    o.device = -1;
+    const double *cols[kMaxParams];
+    for (int j = 0; j < n_params; j++)
+        cols[j] = params + j;
+    double out8[8];
+    if (run_host(kind, 1, &s, &theta, cols, n_params, &o, out8, nullptr, nullptr, -1))
+        return 1;
+    *out = out8[slot];
+    return 0;
+}
+
+int rimphony_b200_compute_cgs(int kind, const double *params, int n_params, int coeff, int stokes, double nu, double b,
+                              double n_e, double theta, double *out)
+{
+    // src/lib.rs:163-173
+    const double nu_c = kElectronCharge * b / (kTwoPi * kMassElectron * kSpeedLight);
+    double val;
+    if (rimphony_b200_compute_dimensionless(kind, params, n_params, coeff, stokes, nu / nu_c, theta, &val))
+        return 1;
+    *out = (coeff == RIMPHONY_B200_EMISSION) ? val * n_e * nu : val * n_e / nu;
+    return 0;
+}
+
+int rimphony_b200_bessel_jn(int64_t count, const double *n, const double *x, double *j, double *dj)
+{
+    if (count < 0 || !n || !x || !j || !dj)
+        return fail("bad arguments");
+    if (count == 0)
+        return 0;
+    DeviceContext *cp = nullptr;
+    if (get_context(-1, &cp))
+        return 1;
+    DeviceContext &c = *cp;
+    std::lock_guard<std::mutex> guard(c.lock);
+    RB_CUDA(cudaSetDevice(c.device));
+    const size_t bytes = (size_t)count * sizeof(double);
+    if (c.in.reserve(2 * bytes) || c.out.reserve(2 * bytes))
+        return 1;
+    double *d_n = static_cast<double *>(c.in.ptr), *d_x = d_n + count;
+    double *d_j = static_cast<double *>(c.out.ptr), *d_dj = d_j + count;
+    RB_CUDA(cudaMemcpyAsync(d_n, n, bytes, cudaMemcpyHostToDevice, c.stream));
+    RB_CUDA(cudaMemcpyAsync(d_x, x, bytes, cudaMemcpyHostToDevice, c.stream));
+    k_bessel<<<(unsigned)((count + 127) / 128), 128, 0, c.stream>>>(count, d_n, d_x, d_j, d_dj);
+    g_launches++;
+    RB_CUDA(cudaGetLastError());
+    RB_CUDA(cudaMemcpyAsync(j, d_j, bytes, cudaMemcpyDeviceToHost, c.stream));
+    RB_CUDA(cudaMemcpyAsync(dj, d_dj, bytes, cudaMemcpyDeviceToHost, c.stream));
+    RB_CUDA(cudaStreamSynchronize(c.stream));
+    return 0;
+}
+
+int rimphony_b200_dist_eval(int kind, const double *params, int n_params, int64_t count, const double *gamma,
+                            const double *cos_xi, double *out3)
+{
+    if (count < 0 || !params || !gamma || !cos_xi || !out3)
+        return fail("bad arguments");
+    if (check_params(kind, n_params))
+        return 1;
+    if (count == 0)
+        return 0;
+    DeviceContext *cp = nullptr;
+    if (get_context(-1, &cp))
+        return 1;
+    DeviceContext &c = *cp;
+    std::lock_guard<std::mutex> guard(c.lock);
+    RB_CUDA(cudaSetDevice(c.device));
+    const size_t bytes = (size_t)count * sizeof(double);
+    if (c.in.reserve(2 * bytes) || c.out.reserve(3 * bytes))
+        return 1;
+    double *d_g = static_cast<double *>(c.in.ptr), *d_c = d_g + count;
+    double *d_o = static_cast<double *>(c.out.ptr);
+    RB_CUDA(cudaMemcpyAsync(d_g, gamma, bytes, cudaMemcpyHostToDevice, c.stream));
+    RB_CUDA(cudaMemcpyAsync(d_c, cos_xi, bytes, cudaMemcpyHostToDevice, c.stream));
+    Dist d;
+    const unsigned grid = (unsigned)((count + 127) / 128);
+    switch (kind) {
+    case RIMPHONY_B200_POWER_LAW:
+        dist_from_params<kDistPowerLaw>(params, n_params, d);
+        k_dist_eval<kDistPowerLaw><<<grid, 128, 0, c.stream>>>(d, count, d_g, d_c, d_o);
+        break;
+    case RIMPHONY_B200_THERMAL_JUETTNER:
+        dist_from_params<kDistThermalJuettner>(params, n_params, d);
+        k_dist_eval<kDistThermalJuettner><<<grid, 128, 0, c.stream>>>(d, count, d_g, d_c, d_o);
+        break;
+    case RIMPHONY_B200_PITCHY_PL:
+        dist_from_params<kDistPitchyPL>(params, n_params, d);
+        k_dist_eval<kDistPitchyPL><<<grid, 128, 0, c.stream>>>(d, count, d_g, d_c, d_o);
+        break;
+    default:
+        dist_from_params<kDistPitchyKappa>(params, n_params, d);
+        k_dist_eval<kDistPitchyKappa><<<grid, 128, 0, c.stream>>>(d, count, d_g, d_c, d_o);
+        break;
+    }
+    g_launches++;
+    RB_CUDA(cudaGetLastError());
+    RB_CUDA(cudaMemcpyAsync(out3, d_o, 3 * bytes, cudaMemcpyDeviceToHost, c.stream));
+    RB_CUDA(cudaStreamSynchronize(c.stream));
+    return 0;
+}
+
+int rimphony_b200_last_kernel_ms(int device, float out_ms[4])
+{
+    if (!out_ms)
+        return fail("null pointer");
+    DeviceContext *cp = nullptr;
+    if (get_context(device, &cp))
+        return 1;
+    memcpy(out_ms, cp->last_ms, sizeof cp->last_ms);
+    return 0;
+}
+
+uint64_t rimphony_b200_kernel_launch_count(void) { return g_launches.load(); }
+
+int rimphony_b200_device_count(void)
+{
+    int count = 0;
+    if (cudaGetDeviceCount(&count) != cudaSuccess)
+        return 0;
+    return count;
+}
+
+int rimphony_b200_abi_version(void) { return RIMPHONY_B200_ABI_VERSION; }
+
+const char *rimphony_b200_last_error(void) { return g_error.c_str(); }
+
+void rimphony_b200_shutdown(void)
+{
+    std::lock_guard<std::mutex> g(g_ctx_lock);
+    for (auto &c : g_ctx) {
+        if (!c.ready)
+            continue;
+        cudaSetDevice(c.device);
+        c.in.release();
+        c.out.release();
+        c.scratch.release();
+        c.counters.release();
+        for (auto &e : c.ev)
+            cudaEventDestroy(e);
+        cudaStreamDestroy(c.stream);
+        cudaStreamDestroy(c.stream_hey);
+        c.ready = false;
+    }
+}
+
+} // extern "C"
