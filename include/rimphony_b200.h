@@ -162,6 +162,11 @@ int rimphony_b200_dist_eval(int kind, const double *params, int n_params, int64_
  * [1] Symphony, [2] Heyvaerts, [3] whole enqueue-to-completion span. */
 int rimphony_b200_last_kernel_ms(int device, float out_ms[4]);
 
+/* Measured FP64 FMA throughput of the device (TFLOP/s, best of 5 runs of a
+ * register-resident DFMA kernel): the roofline denominator for these kernels,
+ * which are bound by the FP64 pipe of the CUDA cores. */
+int rimphony_b200_fp64_peak_tflops(int device, double *out_tflops);
+
 /* Number of kernels this library has launched since it was loaded. */
 uint64_t rimphony_b200_kernel_launch_count(void);
 

@@ -1,0 +1,5 @@
+// explicit instantiation: Symphony kernels, distribution kind 1
+#include "rb_kernels.cuh"
+namespace rbhost {
+template int stage_symphony<rb::kDistThermalJuettner>(const BatchArgs &, bool, int, cudaStream_t);
+}

@@ -25,7 +25,8 @@
 #ifdef __CUDACC__
 #define RB_FN __device__ __forceinline__
 #define RB_HD __host__ __device__ __forceinline__
-#define RB_FN_NOINLINE __device__ __noinline__
+#define RB_FN_NOINLINE static __device__ __noinline__
+#define RB_MFN_NOINLINE __device__ __noinline__
 #define RB_TABLE __constant__ const
 #define RB_DEVICE_BUILD 1
 #else
@@ -35,6 +36,7 @@
 #define RB_FN inline
 #define RB_HD inline
 #define RB_FN_NOINLINE inline __attribute__((noinline))
+#define RB_MFN_NOINLINE inline __attribute__((noinline))
 #define RB_TABLE static const
 #endif
 
@@ -285,6 +287,7 @@ RB_FN void gk31_seq(Warp &w, F &f, double a, double b, GKOut<NV> &o)
     const double half_length = 0.5 * (b - a);
     LaneVals<NV> lv;
     lv.clear();
+#pragma unroll 1
     for (int j = 0; j < 31; j++) {
         double tmp[NV];
         f.eval_collective(w, center + half_length * LANE_X[j], tmp);
@@ -456,6 +459,7 @@ RB_FN void qag_joint(Warp &w, Apply &apply, int n_init, const double *bounds, do
 
     warp_fence(); // previous users of the list storage are done
     L.size = 0;
+#pragma unroll 1
     for (int k = 0; k < n_init; k++) {
         GKOut<NV> o;
         apply(w, bounds[k], bounds[k + 1], o);
@@ -542,9 +546,12 @@ RB_FN void qag_joint(Warp &w, Apply &apply, int n_init, const double *bounds, do
         }
         warp_fence();
 
-        GKOut<NV> o1, o2;
-        apply(w, a1, b1, o1);
-        apply(w, a2, b2, o2);
+        GKOut<NV> o12[2];
+#pragma unroll 1
+        for (int h = 0; h < 2; h++)
+            apply(w, h ? a2 : a1, h ? b2 : b1, o12[h]);
+        const GKOut<NV> &o1 = o12[0];
+        const GKOut<NV> &o2 = o12[1];
 
         const bool too_small = subinterval_too_small(a1, a2, b2);
 
@@ -614,24 +621,32 @@ RB_FN void qag_joint(Warp &w, Apply &apply, int n_init, const double *bounds, do
 // REFINE (single-function, faithful mode) the optimal-step retry of GSL is
 // performed; without it only the first 5-point estimate is used (the joint
 // mode cannot pick a different h per function).
+// Four-point evaluation of gsl's central_deriv: f at x-h, x+h, x-h/2, x+h/2.
+template <int NV, class F>
+RB_FN void deriv_probe(Warp &w, F &f, double x, double h, double (&fv)[4][NV])
+{
+#pragma unroll 1
+    for (int k = 0; k < 4; k++) {
+        const double off = (k == 0) ? -h : (k == 1) ? h : (k == 2) ? -h / 2 : h / 2;
+        f.eval_collective(w, x + off, fv[k]);
+    }
+}
+
 template <int NV, bool REFINE, class F>
 RB_FN void deriv_central_joint(Warp &w, F &f, double x, double h, double (&result)[NV])
 {
-    double fm1[NV], fp1[NV], fmh[NV], fph[NV];
-    f.eval_collective(w, x - h, fm1);
-    f.eval_collective(w, x + h, fp1);
-    f.eval_collective(w, x - h / 2, fmh);
-    f.eval_collective(w, x + h / 2, fph);
+    double fv[4][NV]; // fm1, fp1, fmh, fph
+    deriv_probe<NV, F>(w, f, x, h, fv);
 
     double round0 = 0, trunc0 = 0;
 #pragma unroll
     for (int c = 0; c < NV; c++) {
-        const double r3 = 0.5 * (fp1[c] - fm1[c]);
-        const double r5 = (4.0 / 3.0) * (fph[c] - fmh[c]) - (1.0 / 3.0) * r3;
+        const double r3 = 0.5 * (fv[1][c] - fv[0][c]);
+        const double r5 = (4.0 / 3.0) * (fv[3][c] - fv[2][c]) - (1.0 / 3.0) * r3;
         result[c] = r5 / h;
         if (REFINE && c == 0) {
-            const double e3 = (fabs(fp1[c]) + fabs(fm1[c])) * DBL_EPSILON;
-            const double e5 = 2.0 * (fabs(fph[c]) + fabs(fmh[c])) * DBL_EPSILON + e3;
+            const double e3 = (fabs(fv[1][c]) + fabs(fv[0][c])) * DBL_EPSILON;
+            const double e5 = 2.0 * (fabs(fv[3][c]) + fabs(fv[2][c])) * DBL_EPSILON + e3;
             const double q3 = fabs(r3 / h), q5 = fabs(r5 / h);
             const double dy = (q3 > q5 ? q3 : q5) * (fabs(x) / h) * DBL_EPSILON;
             trunc0 = fabs((r5 - r3) / h);
@@ -643,14 +658,11 @@ RB_FN void deriv_central_joint(Warp &w, F &f, double x, double h, double (&resul
         const double error = round0 + trunc0;
         if (round0 < trunc0 && (round0 > 0 && trunc0 > 0)) {
             const double h_opt = h * cbrt(round0 / (2.0 * trunc0));
-            f.eval_collective(w, x - h_opt, fm1);
-            f.eval_collective(w, x + h_opt, fp1);
-            f.eval_collective(w, x - h_opt / 2, fmh);
-            f.eval_collective(w, x + h_opt / 2, fph);
-            const double r3 = 0.5 * (fp1[0] - fm1[0]);
-            const double r5 = (4.0 / 3.0) * (fph[0] - fmh[0]) - (1.0 / 3.0) * r3;
-            const double e3 = (fabs(fp1[0]) + fabs(fm1[0])) * DBL_EPSILON;
-            const double e5 = 2.0 * (fabs(fph[0]) + fabs(fmh[0])) * DBL_EPSILON + e3;
+            deriv_probe<NV, F>(w, f, x, h_opt, fv);
+            const double r3 = 0.5 * (fv[1][0] - fv[0][0]);
+            const double r5 = (4.0 / 3.0) * (fv[3][0] - fv[2][0]) - (1.0 / 3.0) * r3;
+            const double e3 = (fabs(fv[1][0]) + fabs(fv[0][0])) * DBL_EPSILON;
+            const double e5 = 2.0 * (fabs(fv[3][0]) + fabs(fv[2][0])) * DBL_EPSILON + e3;
             const double q3 = fabs(r3 / h_opt), q5 = fabs(r5 / h_opt);
             const double dy = (q3 > q5 ? q3 : q5) * (fabs(x) / h_opt) * DBL_EPSILON;
             const double error_opt = fabs((r5 - r3) / h_opt) + fabs(e5 / h_opt) + dy;

@@ -163,7 +163,7 @@ struct HeyNROuter {
     double epsrel;
 
     // heyvaerts.rs:213-250
-    RB_FN void eval_collective(Warp &w, double pomega, double (&out)[NV])
+    RB_MFN_NOINLINE void eval_collective(Warp &w, double pomega, double (&out)[NV])
     {
         const double sigma_min = sqrt(pomega * pomega + g->sigma0_sq);
         const double sigma_max = kInverseSqrt3 * sigma_min * sqrt(sigma_min);
@@ -190,7 +190,7 @@ struct HeyQROuter {
     double epsrel;
 
     // heyvaerts.rs:262-296
-    RB_FN void eval_collective(Warp &w, double sigma, double (&out)[NV])
+    RB_MFN_NOINLINE void eval_collective(Warp &w, double sigma, double (&out)[NV])
     {
         const double pomega_max_phys = sqrt(kThreeTwoThirds * cbrt(sigma) * sigma - g->sigma0_sq);
         const double pomega_max_qr = sqrt(sigma * sigma - g->sigma0_sq);
@@ -214,7 +214,7 @@ struct HeyWorkspace {
 //   first_needs_value: the derivative probe and the relative-contribution test
 //   are skipped while the running value is exactly zero (NR right side, QR).
 template <int NV, bool REFINE, class Outer>
-RB_FN void hey_step_outward(Warp &w, Outer &F, IntervalList<NV> &olist, double epsrel_outer, double edge,
+RB_FN_NOINLINE void hey_step_outward(Warp &w, Outer &F, IntervalList<NV> &olist, double epsrel_outer, double edge,
                             double delta, int dir, bool skip_while_zero, double delta_cap, double (&val)[NV],
                             unsigned &alive)
 {

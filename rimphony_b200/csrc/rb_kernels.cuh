@@ -1,0 +1,222 @@
+// rb_kernels.cuh -- the sm_100a kernels and their launch code.  Included by the
+// inst_*.cu translation units only.
+#pragma once
+
+#include "rb_launch.cuh"
+
+namespace rbhost {
+
+// ---------------------------------------------------------------------------
+// kernels
+
+template <int KIND>
+__global__ void __launch_bounds__(kThreadsPerBlock) k_normalize(BatchArgs a)
+{
+    extern __shared__ double smem[];
+    const int warp = threadIdx.x >> 5;
+    double *store = smem + (size_t)warp * kNormCap * IntervalList<1>::doubles_per_interval;
+    Warp w;
+    w.init();
+    const long long stride = (long long)gridDim.x * kWarpsPerBlock;
+    for (long long i = (long long)blockIdx.x * kWarpsPerBlock + warp; i < a.n; i += stride) {
+        w.status = 0;
+        Dist d;
+        double p0;
+        bool ok = load_dist<KIND>(a, i, d, p0);
+        if (ok) {
+            IntervalList<1> list;
+            list.bind(store, kNormCap);
+            ok = dist_normalize<KIND>(w, d, p0, list);
+        }
+        if (w.lane == 0) {
+            a.norm[i] = ok ? d.norm : NAN;
+            if (a.status && (!ok || w.status))
+                atomicOr(&a.status[i], (int)(w.status | (ok ? 0u : kStatusNormFailed)));
+        }
+    }
+}
+
+template <int KIND, bool FUSED>
+__global__ void __launch_bounds__(kThreadsPerBlock, FUSED ? 3 : 4) k_symphony(BatchArgs a)
+{
+    using WS = SymWorkspace<FUSED, kSymGammaCap, kSymNCap>;
+    extern __shared__ double smem[];
+    const int warp = threadIdx.x >> 5;
+    WS &ws = reinterpret_cast<WS *>(smem)[warp];
+    Warp w;
+    w.init();
+
+    for (;;) {
+        const long long i = next_point(a.next, w.lane);
+        if (i >= a.n)
+            break;
+        w.status = 0;
+        w.n_apply_lanes = 0;
+
+        Dist d;
+        double p0;
+        load_dist<KIND>(a, i, d, p0);
+        d.norm = a.norm[i];
+
+        double out6[6], lobes4[4];
+        symphony_point<KIND, FUSED, kSymGammaCap, kSymNCap>(w, d, a.s[i], a.theta[i], a.eps_gamma, a.eps_n, ws, out6,
+                                                            lobes4);
+
+        if (w.lane == 0) {
+            bool any_nan = false;
+#pragma unroll
+            for (int c = 0; c < 6; c++) {
+                if ((a.coeff_mask >> c) & 1u) {
+                    a.out8[(long long)c * a.n + i] = out6[c];
+                    any_nan |= !(out6[c] == out6[c]);
+                }
+            }
+            if (a.lobes4) {
+#pragma unroll
+                for (int c = 0; c < 4; c++)
+                    a.lobes4[(long long)c * a.n + i] = lobes4[c];
+            }
+            if (a.counters)
+                a.counters[i] = w.n_apply_lanes;
+            const unsigned st = w.status | (any_nan ? kStatusNaN : 0u);
+            if (a.status && st)
+                atomicOr(&a.status[i], (int)st);
+        }
+    }
+}
+
+template <int KIND, bool FUSED>
+__global__ void __launch_bounds__(kThreadsPerBlock, 4) k_heyvaerts(BatchArgs a)
+{
+    using WS = HeyWorkspace<FUSED, kHeyInnerCap, kHeyOuterCap>;
+    extern __shared__ double smem[];
+    const int warp = threadIdx.x >> 5;
+    WS &ws = reinterpret_cast<WS *>(smem)[warp];
+    Warp w;
+    w.init();
+
+    for (;;) {
+        const long long i = next_point(a.next, w.lane);
+        if (i >= a.n)
+            break;
+        const double s = a.s[i], theta = a.theta[i];
+        const double sigma0 = s * sin(theta);
+        if (!(sigma0 >= a.sigma0_lo && sigma0 < a.sigma0_hi) && !(a.sigma0_lo < 0.0 && !(sigma0 == sigma0)))
+            continue; // another launch owns this point (NaN sigma0 goes with the lowest band)
+        w.status = 0;
+        w.n_apply_lanes = 0;
+
+        Dist d;
+        double p0;
+        load_dist<KIND>(a, i, d, p0);
+        d.norm = a.norm[i];
+
+        double out2[2];
+        heyvaerts_point<KIND, FUSED, kHeyInnerCap, kHeyOuterCap>(w, d, s, theta, a.eps_hey_inner, a.eps_hey_outer, ws,
+                                                                 out2);
+
+        if (w.lane == 0) {
+            bool any_nan = false;
+#pragma unroll
+            for (int c = 0; c < 2; c++) {
+                if ((a.coeff_mask >> (6 + c)) & 1u) {
+                    a.out8[(long long)(6 + c) * a.n + i] = out2[c];
+                    any_nan |= !(out2[c] == out2[c]);
+                }
+            }
+            if (a.counters)
+                a.counters[a.n + i] = w.n_apply_lanes;
+            const unsigned st = w.status | (any_nan ? kStatusNaN : 0u);
+            if (a.status && st)
+                atomicOr(&a.status[i], (int)st);
+        }
+    }
+}
+
+template <int KIND>
+__global__ void k_dist_eval(Dist d, long long count, const double *gamma, const double *cos_xi, double *out3)
+{
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= count)
+        return;
+    double f, a, b;
+    dist_eval<KIND>(d, gamma[i], cos_xi[i], f, a, b);
+    out3[i] = f;
+    out3[count + i] = a;
+    out3[2 * count + i] = b;
+}
+
+
+// ---------------------------------------------------------------------------
+// stage launchers
+
+template <int KIND>
+int stage_normalize(const BatchArgs &a, int sm_count, cudaStream_t st)
+{
+    const size_t smem = (size_t)kWarpsPerBlock * kNormCap * IntervalList<1>::doubles_per_interval * sizeof(double);
+    int grid = 0;
+    if (set_smem(k_normalize<KIND>, smem) || persistent_grid(k_normalize<KIND>, smem, sm_count, &grid))
+        return 1;
+    const long long need = (a.n + kWarpsPerBlock - 1) / kWarpsPerBlock;
+    if (need < grid)
+        grid = (int)need;
+    k_normalize<KIND><<<grid, kThreadsPerBlock, smem, st>>>(a);
+    g_launches++;
+    RB_CUDA(cudaGetLastError());
+    return 0;
+}
+
+template <int KIND>
+int stage_symphony(const BatchArgs &a, bool faithful, int sm_count, cudaStream_t st)
+{
+    int grid = 0;
+    if (faithful) {
+        const size_t smem = kWarpsPerBlock * sizeof(SymWorkspace<false, kSymGammaCap, kSymNCap>);
+        if (set_smem(k_symphony<KIND, false>, smem) || persistent_grid(k_symphony<KIND, false>, smem, sm_count, &grid))
+            return 1;
+        k_symphony<KIND, false><<<grid, kThreadsPerBlock, smem, st>>>(a);
+    } else {
+        const size_t smem = kWarpsPerBlock * sizeof(SymWorkspace<true, kSymGammaCap, kSymNCap>);
+        if (set_smem(k_symphony<KIND, true>, smem) || persistent_grid(k_symphony<KIND, true>, smem, sm_count, &grid))
+            return 1;
+        k_symphony<KIND, true><<<grid, kThreadsPerBlock, smem, st>>>(a);
+    }
+    g_launches++;
+    RB_CUDA(cudaGetLastError());
+    return 0;
+}
+
+template <int KIND>
+int stage_heyvaerts(const BatchArgs &a, bool fused, int sm_count, cudaStream_t st)
+{
+    int grid = 0;
+    if (!fused) {
+        const size_t smem = kWarpsPerBlock * sizeof(HeyWorkspace<false, kHeyInnerCap, kHeyOuterCap>);
+        if (set_smem(k_heyvaerts<KIND, false>, smem) || persistent_grid(k_heyvaerts<KIND, false>, smem, sm_count, &grid))
+            return 1;
+        k_heyvaerts<KIND, false><<<grid, kThreadsPerBlock, smem, st>>>(a);
+    } else {
+        const size_t smem = kWarpsPerBlock * sizeof(HeyWorkspace<true, kHeyInnerCap, kHeyOuterCap>);
+        if (set_smem(k_heyvaerts<KIND, true>, smem) || persistent_grid(k_heyvaerts<KIND, true>, smem, sm_count, &grid))
+            return 1;
+        k_heyvaerts<KIND, true><<<grid, kThreadsPerBlock, smem, st>>>(a);
+    }
+    g_launches++;
+    RB_CUDA(cudaGetLastError());
+    return 0;
+}
+
+template <int KIND>
+int stage_dist_eval(const double *params, int n_params, long long count, const double *gamma, const double *cos_xi,
+                    double *out3, cudaStream_t st)
+{
+    Dist d;
+    dist_from_params<KIND>(params, n_params, d);
+    d.norm = 1.0;
+    k_dist_eval<KIND><<<(unsigned)((count + 127) / 128), 128, 0, st>>>(d, count, gamma, cos_xi, out3);
+    g_launches++;
+    RB_CUDA(cudaGetLastError());
+    return 0;
+}
+
+} // namespace rbhost

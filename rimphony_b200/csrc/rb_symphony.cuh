@@ -113,7 +113,7 @@ struct SymGammaIntegral {
     int sel;       // accumulator to compute (faithful)
     double epsrel; // relative tolerance of the gamma integral (reference: 1e-3)
 
-    RB_FN void eval_collective(Warp &w, double n, double (&out)[NA])
+    RB_MFN_NOINLINE void eval_collective(Warp &w, double n, double (&out)[NA])
     {
         const double s = g->s, costh = g->cos_th, sinth = g->sin_th;
         const double nos = n / s;

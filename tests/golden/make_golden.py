@@ -1,0 +1,68 @@
+"""Regenerates the oracle fixtures under tests/golden/ (TEST INFRASTRUCTURE).
+
+    python tests/golden/make_golden.py [name ...]
+
+Each fixture holds seeded inputs (rimphony_b200.sampler.synthetic_batch, i.e. the
+configurations of BASELINE.md) and the CPU oracle's outputs for them: the eight
+dimensionless coefficients, the Stokes-V lobes, and the oracle's wall time.  The
+oracle costs ~1 s per point per core, so GPU parity tests read these files
+instead of re-running it; a few points are still recomputed live in the tests.
+
+symphony-powerlaw.txt is the reference's own golden file (tests/symphony-powerlaw.txt:
+200 rows of s, theta, p, J_I, A_I, J_Q, A_Q, J_V, A_V computed with Symphony), copied
+verbatim as data because /root/reference does not exist on the GPU box.
+"""
+import os
+import sys
+import time
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, os.path.dirname(os.path.dirname(HERE)))
+
+from oracle import oracle as O  # noqa: E402
+from rimphony_b200.sampler import synthetic_batch  # noqa: E402
+
+SEED = 20260
+
+FIXTURES = {
+    # name: (config, n points)
+    "pitchy_pl": ("pitchy_pl", 400),
+    "powerlaw": ("powerlaw", 200),
+    "pitchy_kappa": ("pitchy_kappa", 200),
+}
+
+
+def expand(params, n):
+    return [np.broadcast_to(np.asarray(p, dtype=np.float64), (n,)).copy() for p in params]
+
+
+def run(name):
+    t0 = time.time()
+    if name == "symphony_rows":
+        g = np.loadtxt(os.path.join(HERE, "symphony-powerlaw.txt"))
+        kind, s, theta = O.POWER_LAW, g[:, 0].copy(), g[:, 1].copy()
+        params = [g[:, 2].copy(), 1.0, 1e12, 1e10]
+    elif name == "juettner_sweep":
+        kind, s, theta, params = synthetic_batch("juettner_sweep", 0)
+        sel = np.arange(0, len(s), 37)  # 443 of the 16384 grid points
+        s, theta, params = s[sel], theta[sel], [params[0][sel]]
+    else:
+        config, n = FIXTURES[name]
+        kind, s, theta, params = synthetic_batch(config, n, seed=SEED)
+    n = len(s)
+    mask = 0xC0 if name == "juettner_sweep" else 0xFF
+    out, lobes = O.batch(kind, s, theta, params, coeff_mask=mask)
+    dt = time.time() - t0
+    np.savez_compressed(os.path.join(HERE, name + ".npz"), kind=kind, s=s, theta=theta,
+                        params=np.stack(expand(params, n)), out=out, lobes=lobes,
+                        oracle_seconds=dt, oracle_threads=O.num_threads())
+    print(f"{name}: {n} points in {dt:.1f} s on {O.num_threads()} threads "
+          f"({n / dt:.2f} sets/s); NaN fraction per slot {np.isnan(out).mean(axis=1).round(3)}")
+
+
+if __name__ == "__main__":
+    names = sys.argv[1:] or ["symphony_rows", "pitchy_pl", "powerlaw", "pitchy_kappa", "juettner_sweep"]
+    for nm in names:
+        run(nm)

@@ -1,0 +1,340 @@
+"""Parity of the CUDA path against the CPU oracle, through the C ABI (-m gpu).
+
+Tolerances (BASELINE.json north_star: "<= 1e-3 relative, or within the reference's own
+integration tolerance, with sign agreement on rho_Q/V and alpha_V"):
+
+* FAITHFUL mode performs the reference's own sequence of Gauss-Kronrod applications per
+  coefficient: it must agree with the oracle to 1e-6 relative on every finite value and
+  reproduce every NaN (the reference's failure marker) in place.
+* FUSED mode (the product default) converges all integrands on shared nodes.  Both it and
+  the reference then carry an independent integration error of up to the QAG tolerance
+  (epsrel = 1e-3 per nested level, symphony.rs:266, 376), so the bar is
+    - I and Q coefficients: <= 1e-3 relative on >= 99 % of points and <= 2.5e-3 on all;
+    - Stokes V (two lobes integrated separately that nearly cancel, symphony.rs:97-107):
+      |gpu - oracle| <= 1e-3 * (|lobe+| + |lobe-|), the reference's own integration scale;
+    - rho_Q, rho_V: exact-sequence parity for s sin(theta) < 3 (the kernel switches to the
+      faithful sequence there), <= 1e-3 on >= 99 % and <= 3e-3 on all points above.
+"""
+import math
+
+import numpy as np
+import pytest
+
+import rimphony_b200 as R
+
+pytestmark = pytest.mark.gpu
+
+NAMES = R.COEFFICIENT_NAMES
+FIXTURES = ["pitchy_pl", "powerlaw", "pitchy_kappa", "symphony_rows"]
+
+
+def run(fx, mode, mask=0xFF, extras=True, **kw):
+    return R.compute_all_dimensionless_batch(fx["kind"], fx["s"], fx["theta"], fx["params"], mode=mode,
+                                             coeff_mask=mask, extras=extras, **kw)
+
+
+def finite_pairs(a, b):
+    return ~np.isnan(a) & ~np.isnan(b)
+
+
+# --- kernel 2: the Leung Bessel evaluator ---------------------------------------------
+
+def test_device_bessel_matches_reference_bessel_c(oracle):
+    rng = np.random.default_rng(0)
+    m = 30000
+    n = 10 ** rng.uniform(math.log10(30), 10, m)
+    n[::3] = np.floor(n[::3])
+    eps = 10 ** rng.uniform(-12, 0, m)
+    x = n * (1 - eps)
+    # the integer-order branch (gsl_sf_bessel_Jn in the reference, bessel.c:327-334)
+    n[:4000] = np.floor(rng.uniform(0, 30, 4000))
+    x[:4000] = rng.uniform(0, 1, 4000) * (n[:4000] + 1)
+    # x > n: Debye / blend / Meissel-2
+    x[4000:6000] = n[4000:6000] * (1 + 10 ** rng.uniform(-10, 0.3, 2000))
+    j, dj = R.bessel_jn(n, x)
+    rj = np.array([oracle.ref_bessel_j(a, b) for a, b in zip(n, x)])
+    rdj = np.array([oracle.ref_bessel_dj(a, b) for a, b in zip(n, x)])
+    assert np.array_equal(np.isnan(j), np.isnan(rj)) and np.array_equal(np.isnan(dj), np.isnan(rdj))
+    for got, want in ((j, rj), (dj, rdj)):
+        sig = np.abs(want) > 1e-250
+        rel = np.abs(got[sig] / want[sig] - 1)
+        # the exponent n (ln(..) - ..) - lgamma(n) carries ~ulp(n ln n) of rounding noise in BOTH
+        # implementations (1e-6 at n = 1e10), amplified in J' by the n J_n/x - J_{n+1} difference
+        assert np.median(rel) < 1e-14
+        assert np.percentile(rel, 99) < 1e-8
+        assert rel.max() < 2e-3
+    small = slice(0, 4000)
+    ok = np.abs(rj[small]) > 1e-280
+    assert np.abs(j[small][ok] / rj[small][ok] - 1).max() < 1e-10
+
+
+def test_device_bessel_special_arguments():
+    j, dj = R.bessel_jn(np.array([0.0, 5.0, 0.0, 29.5, -1.0, 40.0, 1e15, 1.0, 0.0]),
+                        np.array([0.0, 5.0, 17.0, 3.0, 2.0, 0.0, 1e14, 0.0, 0.0]))
+    assert abs(j[0] - 1.0) < 1e-6 and abs(j[1] - 0.2611405) < 1e-6 and abs(j[2] + 0.1698543) < 1e-6  # lib.rs:83-85
+    assert math.isnan(j[3]) and math.isnan(j[4])       # non-integer n < 30, negative n (bessel.c:323-331)
+    assert j[5] == 0.0 and dj[5] == 0.0                 # x = 0, n >= 2 (bessel.c:393-395)
+    assert math.isnan(dj[6])                            # n >= 1e15 (bessel.c:382-388)
+    assert dj[8] == 0.0 or abs(dj[8]) < 1e-300          # J_0'(0) = -J_1(0) = 0
+
+
+# --- distributions and normalisation ---------------------------------------------------
+
+@pytest.mark.parametrize("kind,params", [(R.POWER_LAW, [2.5, 1.0, 1e12, 1e10]), (R.THERMAL_JUETTNER, [10.0]),
+                                         (R.PITCHY_PL, [3.1, 1.7, 1.0, 1e12, 1e10]), (R.PITCHY_KAPPA, [2.7, 5.0, 0.8, 1e10])])
+def test_distribution_functions(oracle, kind, params):
+    import ctypes
+    rng = np.random.default_rng(1)
+    gamma = 1.0 + 10 ** rng.uniform(-3, 6, 2000)
+    cx = rng.uniform(-0.99, 0.99, 2000)
+    f, dg, dc = R.dist_eval(kind, params, gamma, cx)
+    d = oracle.make_dist(kind, params)
+    d.norm = 1.0
+    a, b = ctypes.c_double(), ctypes.c_double()
+    L = oracle.lib()
+    for i in range(0, 2000, 7):
+        want_f = L.orc_calc_f(ctypes.byref(d), gamma[i], cx[i])
+        L.orc_calc_f_derivatives(ctypes.byref(d), gamma[i], cx[i], ctypes.byref(a), ctypes.byref(b))
+        assert f[i] == pytest.approx(want_f, rel=1e-12, abs=1e-300)
+        assert dg[i] == pytest.approx(a.value, rel=1e-11, abs=1e-300)
+        assert dc[i] == pytest.approx(b.value, rel=1e-11, abs=1e-300)
+
+
+def test_hard_gamma_cutoffs_are_exact_zero():
+    f, dg, dc = R.dist_eval(R.POWER_LAW, [2.5, 10.0, 1e3, 1e10], np.array([9.999, 10.0, 1e3, 1000.001]), np.zeros(4))
+    assert f[0] == 0.0 and f[3] == 0.0 and f[1] > 0 and f[2] > 0 and dg[0] == 0.0  # power_law.rs:38, 49
+
+
+@pytest.mark.parametrize("name", ["pitchy_pl", "powerlaw", "pitchy_kappa", "juettner_sweep"])
+def test_normalisation_matches_oracle(oracle, golden, name):
+    fx = golden(name)
+    sel = np.arange(0, len(fx["s"]), max(1, len(fx["s"]) // 40))
+    sub = {"kind": fx["kind"], "s": fx["s"][sel], "theta": fx["theta"][sel], "params": [p[sel] for p in fx["params"]]}
+    res = run(sub, R.MODE_FUSED, mask=0x01)
+    for i in range(len(sel)):
+        d = oracle.make_dist(fx["kind"], [p[i] for p in sub["params"]])
+        assert res.norm[i] == pytest.approx(d.norm, rel=1e-10)
+
+
+# --- the hot path: faithful mode is the reference's algorithm ------------------------------
+
+@pytest.mark.parametrize("name", FIXTURES)
+def test_faithful_mode_reproduces_the_oracle(golden, name):
+    fx = golden(name)
+    res = run(fx, R.MODE_FAITHFUL)
+    want = fx["out"]
+    for c in range(8):
+        got_c, want_c = res.values[c], want[c]
+        assert np.array_equal(np.isnan(got_c), np.isnan(want_c)), f"NaN pattern differs for {NAMES[c]}"
+        ok = finite_pairs(got_c, want_c)
+        rel = np.abs(got_c[ok] / want_c[ok] - 1)
+        assert rel.max() < 1e-6, (NAMES[c], rel.max(), np.argmax(rel))
+        assert np.median(rel) < 1e-12
+    ok = ~np.isnan(fx["lobes"]).any(axis=0)
+    assert np.allclose(res.lobes[:, ok], fx["lobes"][:, ok], rtol=1e-6, atol=0.0)
+    assert ((res.status & R.STATUS_NAN) != 0).tolist() == np.isnan(res.values).any(axis=0).tolist()
+    assert (res.status & R.STATUS_CAP_HIT).sum() == 0
+
+
+def test_faithful_juettner_faraday_sweep(golden):
+    fx = golden("juettner_sweep")
+    res = run(fx, R.MODE_FAITHFUL, mask=0xC0)
+    for c in (6, 7):
+        assert np.array_equal(np.isnan(res.values[c]), np.isnan(fx["out"][c]))
+        ok = finite_pairs(res.values[c], fx["out"][c])
+        assert np.abs(res.values[c][ok] / fx["out"][c][ok] - 1).max() < 1e-6
+    assert np.isnan(res.values[:6]).all()  # slots that were not requested come back as NaN
+
+
+# --- the hot path: fused mode (the product) --------------------------------------------------
+
+@pytest.mark.parametrize("name", FIXTURES)
+def test_fused_mode_within_the_integration_tolerance(golden, name):
+    fx = golden(name)
+    res = run(fx, R.MODE_FUSED)
+    want, lobes = fx["out"], fx["lobes"]
+    sigma0 = fx["s"] * np.sin(fx["theta"])
+
+    for c in range(4):  # j_I, alpha_I, j_Q, alpha_Q
+        assert np.array_equal(np.isnan(res.values[c]), np.isnan(want[c])), NAMES[c]
+        ok = finite_pairs(res.values[c], want[c])
+        rel = np.abs(res.values[c][ok] / want[c][ok] - 1)
+        assert (rel <= 1e-3).mean() >= 0.99, (NAMES[c], (rel <= 1e-3).mean())
+        assert rel.max() <= 2.5e-3, (NAMES[c], rel.max())
+        assert (np.sign(res.values[c][ok]) == np.sign(want[c][ok])).all()
+
+    for c, (lp, lm) in ((4, (0, 1)), (5, (2, 3))):  # Stokes V against the lobe scale
+        assert np.array_equal(np.isnan(res.values[c]), np.isnan(want[c])), NAMES[c]
+        ok = finite_pairs(res.values[c], want[c])
+        scale = np.abs(lobes[lp]) + np.abs(lobes[lm])
+        err = np.abs(res.values[c] - want[c])[ok] / scale[ok]
+        assert err.max() <= 1e-3, (NAMES[c], err.max())
+        # sign agreement wherever the reference's V is resolved above its own integration noise
+        resolved = ok & (np.abs(want[c]) > 4e-3 * scale)
+        assert (np.sign(res.values[c][resolved]) == np.sign(want[c][resolved])).all()
+
+    for c in (6, 7):  # Faraday
+        low = sigma0 < 3.0
+        # exact-sequence parity where the reference's answer depends on the sequence
+        assert np.array_equal(np.isnan(res.values[c][low]), np.isnan(want[c][low])), NAMES[c]
+        ok = finite_pairs(res.values[c], want[c]) & low
+        if ok.any():
+            assert np.abs(res.values[c][ok] / want[c][ok] - 1).max() < 1e-6
+        hi = ~low
+        assert np.array_equal(np.isnan(res.values[c][hi]), np.isnan(want[c][hi])), NAMES[c]
+        ok = finite_pairs(res.values[c], want[c]) & hi
+        if ok.any():
+            rel = np.abs(res.values[c][ok] / want[c][ok] - 1)
+            assert (rel <= 1e-3).mean() >= 0.99, (NAMES[c], (rel <= 1e-3).mean())
+            assert rel.max() <= 3e-3, (NAMES[c], rel.max())
+            assert (np.sign(res.values[c][ok]) == np.sign(want[c][ok])).all()
+
+
+def test_fused_mode_against_the_symphony_golden_file(golden, symphony_rows):
+    """tests/symphony.rs: six coefficients vs Symphony itself at 1 % (cgs at nu = 1e9, n_e = 1)."""
+    g = symphony_rows
+    nu = 1e9
+    b = R.TWO_PI * R.MASS_ELECTRON * R.SPEED_LIGHT * nu / (R.ELECTRON_CHARGE * g[:, 0])  # symphony.rs:54
+    calc = R.PowerLawDistribution(g[:, 2]).gamma_limits(1.0, 1e12, 1e10).full_calculation()
+    ours = calc.compute_all_cgs(nu, b, 1.0, g[:, 1])
+    rel = np.abs(ours[:, :6] / g[:, 3:9] - 1)
+    assert rel[:, :4].max() < 2e-3
+    assert (rel[:, 4:] < 0.01).mean() > 0.99 and rel[:, 4:].max() < 0.015
+
+
+def test_live_oracle_on_seeded_points(oracle):
+    """A handful of points the fixtures do not contain, oracle run now."""
+    kind, s, theta, params = R.synthetic_batch("pitchy_pl", 8, seed=987)
+    want, lobes = oracle.batch(kind, s, theta, params)
+    got = R.compute_all_dimensionless_batch(kind, s, theta, params, mode=R.MODE_FAITHFUL).values
+    assert np.array_equal(np.isnan(got), np.isnan(want))
+    ok = ~np.isnan(want)
+    assert np.abs(got[ok] / want[ok] - 1).max() < 1e-6
+
+
+# --- known answers through the reference-shaped API ------------------------------------------
+
+def test_one_powerlaw_direct():
+    """examples/one-powerlaw-direct.rs."""
+    ji = (R.PowerLawDistribution(2.5).gamma_limits(1.0, 1e12, 1e10).full_calculation()
+          .compute_cgs(R.Coefficient.Emission, R.Stokes.I, 1e9, 1e3, 1.0, 0.9))
+    assert isinstance(ji, float) and abs(ji / 2.64399749412774e-21 - 1) < 0.01
+
+
+@pytest.mark.parametrize("mode", [R.MODE_FUSED, R.MODE_FAITHFUL])
+def test_heyvaerts_known_answers(mode):
+    C, S = R.Coefficient, R.Stokes
+    pl = R.PowerLawDistribution(2.5).gamma_limits(10.0, 1e12, 1e10).full_calculation(mode=mode)
+    assert pl.compute_dimensionless(C.Faraday, S.Q, 1e4, 0.25 * math.pi) == pytest.approx(1.89e-9, rel=0.01)   # power_law.rs:209-216
+    assert pl.compute_dimensionless(C.Faraday, S.V, 1e4, 0.25 * math.pi) == pytest.approx(5.28e-8, rel=0.01)   # power_law.rs:233-240
+    assert (R.ThermalJuettnerDistribution(10.0).full_calculation(mode=mode)
+            .compute_dimensionless(C.Faraday, S.Q, 4e4, 0.4)) == pytest.approx(4.8081e-11, rel=0.01)           # thermal_juettner.rs:183-190
+    assert (R.ThermalJuettnerDistribution(0.1).full_calculation(mode=mode)
+            .compute_dimensionless(C.Faraday, S.V, 40.0, 0.5)) == pytest.approx(3.064e-4, rel=0.01)            # thermal_juettner.rs:203-210
+
+
+def test_scalar_c_abi_entry_points():
+    import ctypes
+    from rimphony_b200 import _lib
+    L = _lib.load()
+    pv = (ctypes.c_double * 4)(2.5, 1.0, 1e12, 1e10)
+    out = ctypes.c_double()
+    _lib.check(L.rimphony_b200_compute_cgs(R.POWER_LAW, pv, 4, 0, 0, 1e9, 1e3, 1.0, 0.9, ctypes.byref(out)))
+    assert abs(out.value / 2.64399749412774e-21 - 1) < 0.01
+    _lib.check(L.rimphony_b200_compute_dimensionless(R.POWER_LAW, pv, 4, 2, 0, 10.0, 0.5, ctypes.byref(out)))
+    assert math.isnan(out.value)  # (Faraday, I)
+
+
+def test_pitchy_k_zero_equals_isotropic():
+    """pitchy_pl.rs:128-201: the Latin square of (s, theta, p), all eight coefficients."""
+    ss = np.array([1e0, 1e1, 1e2, 1e3, 1e4])
+    thetas = np.array([0.05, 0.430, 0.810, 1.190, 1.5707])
+    ps = np.array([1.5, 1.75, 2.5, 3.25, 4.0])
+    choices = [1, 4, 2, 3, 1, 0, 0, 3, 1, 2, 0, 4, 4, 2, 3]
+    s = ss[choices[0::3]]
+    th = thetas[choices[1::3]]
+    p = ps[choices[2::3]]
+    iso = R.PowerLawDistribution(p).full_calculation().compute_all_dimensionless(s, th)
+    pit = R.PitchyPowerLawDistribution(p, 0.0).full_calculation().compute_all_dimensionless(s, th)
+    assert iso.shape == (5, 8)
+    assert np.array_equal(np.isnan(iso), np.isnan(pit))
+    ok = ~np.isnan(iso)
+    assert np.abs(pit[ok] / iso[ok] - 1).max() < 1e-9
+
+
+# --- batch semantics and size-independent properties --------------------------------------
+
+def test_empty_single_and_ragged_batches():
+    kind, s, theta, params = R.synthetic_batch("pitchy_pl", 131, seed=3)
+    full = R.compute_all_dimensionless_batch(kind, s, theta, params).values
+    assert R.compute_all_dimensionless_batch(kind, s[:0], theta[:0], [p[:0] if np.ndim(p) else p for p in params]).values.shape == (8, 0)
+    for n in (1, 31, 33, 130):
+        part = R.compute_all_dimensionless_batch(kind, s[:n], theta[:n], [p[:n] if np.ndim(p) else p for p in params]).values
+        assert np.array_equal(part, full[:, :n], equal_nan=True)
+
+
+def test_results_do_not_depend_on_batch_order_or_composition():
+    """Points are independent: any permutation or split of the batch gives bitwise the same values,
+    and so does running it twice (no races in the shared-memory interval lists)."""
+    kind, s, theta, params = R.synthetic_batch("pitchy_pl", 4096, seed=11)
+    a = R.compute_all_dimensionless_batch(kind, s, theta, params, extras=True)
+    b = R.compute_all_dimensionless_batch(kind, s, theta, params, extras=True)
+    assert np.array_equal(a.values, b.values, equal_nan=True) and np.array_equal(a.status, b.status)
+    perm = np.random.default_rng(0).permutation(len(s))
+    pp = [p[perm] if np.ndim(p) else p for p in params]
+    c = R.compute_all_dimensionless_batch(kind, s[perm], theta[perm], pp)
+    assert np.array_equal(c.values, a.values[:, perm], equal_nan=True)
+    # symphony slots never fail on this envelope; Faraday NaNs only in the s sin(theta) < 3 corner
+    assert not np.isnan(a.values[:6]).any()
+    sigma0 = s * np.sin(theta)
+    assert not np.isnan(a.values[6:, sigma0 >= 3.0]).any()
+    assert ((a.status & R.STATUS_NAN) != 0).tolist() == np.isnan(a.values).any(axis=0).tolist()
+    assert (a.status & R.STATUS_CAP_HIT).mean() < 0.002
+    # physics: |j_Q| <= j_I, |j_V| <= j_I, j_I > 0, alpha_V is the sum of its lobes
+    assert (a.values[0] > 0).all() and (np.abs(a.values[2]) <= a.values[0]).all() and (np.abs(a.values[4]) <= a.values[0]).all()
+    assert np.allclose(a.lobes[0] + a.lobes[1], a.values[4], rtol=1e-12, atol=0) and np.allclose(a.lobes[2] + a.lobes[3], a.values[5], rtol=1e-12, atol=0)
+
+
+def test_coefficient_mask_and_broadcast_parameters():
+    kind, s, theta, params = R.synthetic_batch("pitchy_pl", 64, seed=5)
+    full = R.compute_all_dimensionless_batch(kind, s, theta, params).values
+    only = R.compute_all_dimensionless_batch(kind, s, theta, params, coeff_mask=(1 << 2) | (1 << 7)).values
+    assert np.array_equal(only[2], full[2], equal_nan=True) and np.array_equal(only[7], full[7], equal_nan=True)
+    assert np.isnan(only[[0, 1, 3, 4, 5, 6]]).all()
+    expanded = [np.full(len(s), p) if not np.ndim(p) else p for p in params]
+    again = R.compute_all_dimensionless_batch(kind, s, theta, expanded).values
+    assert np.array_equal(again, full, equal_nan=True)
+    short = R.compute_all_dimensionless_batch(kind, s, theta, params[:2]).values  # trailing defaults of pitchy_pl.rs:73-82
+    assert np.array_equal(short, full, equal_nan=True)
+
+
+def test_device_pointer_path_and_multi_entry_agree_with_host_path():
+    import torch
+    kind, s, theta, params = R.synthetic_batch("powerlaw", 257, seed=2)
+    host = R.compute_all_dimensionless_batch(kind, s, theta, params)
+    dev = torch.device("cuda", 0)
+    d_s, d_t = torch.from_numpy(s).to(dev), torch.from_numpy(theta).to(dev)
+    d_p = [torch.from_numpy(np.atleast_1d(np.asarray(p, dtype=np.float64))).to(dev) for p in params]
+    d_out = torch.empty(8 * len(s), dtype=torch.float64, device=dev)
+    d_status = torch.zeros(len(s), dtype=torch.int32, device=dev)
+    with torch.cuda.device(dev):
+        R.compute_all_dimensionless_device(kind, d_s, d_t, d_p, d_out, d_status, stream=torch.cuda.current_stream())
+    assert np.array_equal(d_out.cpu().numpy().reshape(8, -1), host.values, equal_nan=True)
+    assert np.array_equal(d_status.cpu().numpy(), host.status)
+    multi = R.compute_all_dimensionless_batch(kind, s, theta, params, n_devices=0)
+    assert np.array_equal(multi.values, host.values, equal_nan=True) and np.array_equal(multi.status, host.status)
+
+
+def test_high_harmonic_corner_runs_and_is_finite():
+    """BASELINE C4: s >= 1e5 (rel_width switch at s >= 1e6, symphony.rs:337-341)."""
+    s = np.array([1e5, 3e5, 1e6, 3e6, 1e7])
+    theta = np.array([0.8, 0.3, 1.2, 0.05, 0.8])
+    calc = R.PitchyKappaDistribution(3.0, 5.0, 1.0).gamma_cutoff(1e10).full_calculation()
+    res = calc.compute_all_dimensionless_batch(s, theta, extras=True)
+    assert np.isfinite(res.values[:6]).all()
+    assert (res.values[0] > 0).all()
+
+
+def test_graft_entry_smoke():
+    import __graft_entry__ as g
+    g.smoke()
