@@ -214,13 +214,17 @@ def main():
     d_out = torch.empty(8 * n, dtype=torch.float64, device=dev)
     d_status = torch.zeros(n, dtype=torch.int32, device=dev)
     flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=dev)  # > 126 MB L2
-    stream = torch.cuda.current_stream()
+    # a real (non-default) stream: the library launches on the stream it is handed, and the
+    # CUDA events below must be recorded on that same stream to see the kernels
+    stream = torch.cuda.Stream(device=dev)
 
     def step_device():
-        flush.fill_(1)
-        R.compute_all_dimensionless_device(kind, d_s, d_theta, d_params, d_out, d_status, stream=stream,
-                                           synchronize=False)
+        with torch.cuda.stream(stream):
+            flush.fill_(1)
+            R.compute_all_dimensionless_device(kind, d_s, d_theta, d_params, d_out, d_status, stream=stream,
+                                               synchronize=False)
 
+    torch.cuda.synchronize()
     for _ in range(args.warmup):
         step_device()
     barrier()

@@ -1,0 +1,251 @@
+// rb_engine.cuh -- the compact warp-cooperative quadrature engine of the
+// product ("fast") path.
+//
+// One warp owns one parameter point.  The building block is one 31-point
+// Gauss-Kronrod application of up to eight integrands ("channels") that share
+// their nodes:
+//
+//   * lanes-as-nodes: lane j evaluates every channel at node j and stores the
+//     pre-weighted values  A = wk_j f_j  and  B = (wk_j - wg_j) f_j  into a
+//     [channel][node] tile of the warp's shared memory;
+//   * lanes-as-channels: lane L = 4 c + q then sums a quarter of channel c's row
+//     (8 conflict-free LDS.64 per tile), two xor-shuffles finish the sums, and the
+//     Kronrod estimate, the |K - G| error estimate and the acceptance test of
+//     channel c are ordinary per-lane scalar code on lanes 4c..4c+3.
+//
+// So nothing on the bookkeeping side is unrolled over channels: eight integrals
+// are converged by eight lane groups in SIMD, and a warp vote decides whether
+// the panel is accepted or bisected.  The adaptive driver is "local" (a stack of
+// pending panels in shared memory, each accepted on its own error estimate),
+// which needs no interval list, no arg-max and no stored partial results.  The
+// same driver runs both quadrature levels: at the outer level the 31 node values
+// are themselves inner integrals, computed one after the other and parked in
+// the outer tile.
+//
+// This replaces the reference's use of GSL QAG (src/gsl.rs:169-180) on the
+// product path; the QUADPACK-faithful list-based driver (rb_core.cuh
+// qag_joint<>) remains the parity anchor of MODE_FAITHFUL.  Design notes:
+// DESIGN.md section 4.
+//
+// Like rb_core.cuh this header also compiles under g++ with -DRB_HOST_EMU
+// (development harness only): lanes and channels become explicit loops.
+#pragma once
+
+#include "rb_core.cuh"
+
+namespace rb {
+
+constexpr int kEngChan = 8;         // channels per tile
+constexpr int kEngRow = 36;         // padded row length: node j sits at column j + (j >> 3), so that the
+                                    // four quarter rows of four channels hit 16 distinct 8-byte banks
+constexpr int kEngStack = 24;       // pending panels per level
+constexpr int kEngTile = 2 * kEngChan * kEngRow; // doubles per tile (A rows then B rows)
+
+// per-warp shared-memory working set of one quadrature level
+struct EngLevel {
+    double tile[kEngTile];
+    double stk_a[kEngStack];
+    double stk_b[kEngStack];
+    int stk_tag[kEngStack];
+};
+
+// Per-channel state: one register on the device (the lane's own channel), an
+// array in the host emulation.
+template <class T>
+struct PerChan {
+#ifdef RB_DEVICE_BUILD
+    T v;
+    RB_FN T &operator[](int) { return v; }
+    RB_FN const T &operator[](int) const { return v; }
+#else
+    T v[kEngChan];
+    RB_FN T &operator[](int c) { return v[c]; }
+    RB_FN const T &operator[](int c) const { return v[c]; }
+#endif
+};
+
+#ifdef RB_DEVICE_BUILD
+// the body runs once, for the lane's own channel
+#define RB_FOR_CHAN(c, nv) for (int c = (threadIdx.x & 31) >> 2, rb_once_ = 1; rb_once_ && c < (nv); rb_once_ = 0)
+#else
+#define RB_FOR_CHAN(c, nv) for (int c = 0; c < (nv); c++)
+#endif
+
+// Value of channel `c` made warp-uniform (read from the first lane of its group).
+RB_FN double chan_get(const PerChan<double> &x, int c)
+{
+#ifdef RB_DEVICE_BUILD
+    return __shfl_sync(0xffffffffu, x.v, 4 * c);
+#else
+    return x.v[c];
+#endif
+}
+
+// Kronrod - Gauss weight difference per lane (B rows of the tile).
+RB_TABLE double LANE_WD[32] = {
+    0.005377479872923348987792051430128,  0.015007947329316122538374763075807 - 0.030753241996117268354628393577204,
+    0.025460847326715320186874001019653,  0.035346360791375846222037948478360 - 0.070366047488108124709267416450667,
+    0.044589751324764876608227299373280,  0.053481524690928087265343147239430 - 0.107159220467171935011869546685869,
+    0.062009567800670640285139230960803,  0.069854121318728258709520077099147 - 0.139570677926154314447804794511028,
+    0.076849680757720378894432777482659,  0.083080502823133021038289247286104 - 0.166269205816993933553200860481209,
+    0.088564443056211770647275443693774,  0.093126598170825321225486872747346 - 0.186161000015562211026800561866423,
+    0.096642726983623678505179907627589,  0.099173598721791959332393173484603 - 0.198431485327111576456118326443839,
+    0.100769845523875595044946662617570,  0.101330007014791549017374792767493 - 0.202578241925561272880620199967519,
+    0.100769845523875595044946662617570,  0.099173598721791959332393173484603 - 0.198431485327111576456118326443839,
+    0.096642726983623678505179907627589,  0.093126598170825321225486872747346 - 0.186161000015562211026800561866423,
+    0.088564443056211770647275443693774,  0.083080502823133021038289247286104 - 0.166269205816993933553200860481209,
+    0.076849680757720378894432777482659,  0.069854121318728258709520077099147 - 0.139570677926154314447804794511028,
+    0.062009567800670640285139230960803,  0.053481524690928087265343147239430 - 0.107159220467171935011869546685869,
+    0.044589751324764876608227299373280,  0.035346360791375846222037948478360 - 0.070366047488108124709267416450667,
+    0.025460847326715320186874001019653,  0.015007947329316122538374763075807 - 0.030753241996117268354628393577204,
+    0.005377479872923348987792051430128,  0.0};
+
+RB_FN int tile_col(int node) { return node + (node >> 3); }
+
+// Store the node values of one lane (node = lane) into a tile, pre-weighted.
+template <int NV>
+RB_FN void tile_store(double *tile, const Warp &w, int node, const double (&vals)[NV])
+{
+#ifdef RB_DEVICE_BUILD
+    const double wk = w.wk; // the lane's own weights live in registers
+    const double wd = w.wk - w.wg;
+#else
+    (void)w;
+    const double wk = LANE_WK[node];
+    const double wd = LANE_WD[node];
+#endif
+    const int col = tile_col(node);
+#pragma unroll
+    for (int c = 0; c < NV; c++) {
+        const double f = (node < 31) ? vals[c] : 0.0;
+        tile[c * kEngRow + col] = wk * f;
+        tile[(kEngChan + c) * kEngRow + col] = wd * f;
+    }
+}
+
+// Reduce a tile: per channel the Kronrod estimate r of the integral over a panel
+// of half-length `hl` and an error estimate e.  The estimate is QUADPACK's
+// (200 |K - G| / scale)^1.5 heuristic with the integral of |f| as the scale (the
+// reference's second pass for the integral of |f - mean| is not needed at the
+// tolerances of this path), floored at 50 ulp of the integral of |f|.
+RB_FN_NOINLINE void tile_reduce(const double *tile, int nv, double hl, PerChan<double> &r, PerChan<double> &e)
+{
+#ifdef RB_DEVICE_BUILD
+    const int lane = threadIdx.x & 31;
+    const int c = lane >> 2, q = lane & 3;
+    double k = 0.0, d = 0.0, a = 0.0;
+    if (c < nv) {
+        const double *ra = tile + c * kEngRow + 9 * q;
+        const double *rb = ra + kEngChan * kEngRow;
+#pragma unroll
+        for (int t = 0; t < 8; t++) {
+            const double va = ra[t];
+            k += va;
+            a += fabs(va);
+            d += rb[t];
+        }
+    }
+    k += __shfl_xor_sync(0xffffffffu, k, 1);
+    d += __shfl_xor_sync(0xffffffffu, d, 1);
+    a += __shfl_xor_sync(0xffffffffu, a, 1);
+    k += __shfl_xor_sync(0xffffffffu, k, 2);
+    d += __shfl_xor_sync(0xffffffffu, d, 2);
+    a += __shfl_xor_sync(0xffffffffu, a, 2);
+    {
+#else
+    for (int c = 0; c < nv; c++) {
+        double k = 0.0, d = 0.0, a = 0.0;
+        for (int q = 0; q < 4; q++) {
+            double kq = 0.0, dq = 0.0, aq = 0.0;
+            for (int t = 0; t < 8; t++) {
+                const double va = tile[c * kEngRow + 9 * q + t];
+                kq += va;
+                aq += fabs(va);
+                dq += tile[(kEngChan + c) * kEngRow + 9 * q + t];
+            }
+            k += kq;
+            d += dq;
+            a += aq;
+        }
+#endif
+        const double ahl = fabs(hl);
+        const double rabs = a * ahl;
+        double err = fabs(d * hl);
+        if (rabs != 0.0 && err != 0.0) {
+            const double qq = 200.0 * err / rabs;
+            const double scale = qq * sqrt(qq);
+            err = (scale < 1.0) ? rabs * scale : rabs;
+        }
+        const double min_err = 50.0 * DBL_EPSILON * rabs;
+        if (min_err > err)
+            err = min_err;
+        r[c] = k * hl;
+        e[c] = err;
+    }
+}
+
+// Warp vote over the channels 0..nv-1.
+RB_FN bool chan_all(const PerChan<bool> &ok, int nv)
+{
+#ifdef RB_DEVICE_BUILD
+    const int c = (threadIdx.x & 31) >> 2;
+    return __all_sync(0xffffffffu, ok.v || c >= nv);
+#else
+    bool all = true;
+    for (int c = 0; c < nv; c++)
+        all = all && ok.v[c];
+    return all;
+#endif
+}
+
+// A pending-panel stack (warp-uniform; lane 0 writes, everybody reads).
+struct PanelStack {
+    EngLevel *lv;
+    int sp;
+
+    RB_FN void reset(EngLevel *level)
+    {
+        lv = level;
+        sp = 0;
+        warp_fence();
+    }
+    RB_FN bool room(int k) const { return sp + k <= kEngStack; }
+    RB_FN void push(const Warp &w, double a, double b, int tag)
+    {
+#ifdef RB_DEVICE_BUILD
+        if (w.lane == 0)
+#endif
+        {
+            lv->stk_a[sp] = a;
+            lv->stk_b[sp] = b;
+            lv->stk_tag[sp] = tag;
+        }
+        sp++;
+    }
+    RB_FN void seal() const { warp_fence(); } // make pushes visible before the next pop
+    RB_FN void pop(double &a, double &b, int &tag)
+    {
+        sp--;
+        a = lv->stk_a[sp];
+        b = lv->stk_b[sp];
+        tag = lv->stk_tag[sp];
+    }
+};
+
+// The acceptance rule of a panel for one channel: the error estimate is within
+// `epsrel` of the larger of the panel's own value and `floor` (a fraction of the
+// magnitude of the whole integral as known so far).  NaN compares as accepted so
+// that it propagates into the sum, which is how the reference reports failure.
+RB_FN bool panel_ok(double r, double e, double epsrel, double floor)
+{
+    const double m = fmax(fabs(r), floor);
+    return !(e > epsrel * m);
+}
+
+RB_FN bool panel_too_small(double a, double b)
+{
+    const double m = fmax(fabs(a), fabs(b));
+    return !(fabs(b - a) > 64.0 * DBL_EPSILON * m);
+}
+
+} // namespace rb

@@ -208,7 +208,9 @@ template <int KIND>
 int launch_kind(DeviceContext &c, BatchArgs a, const ResolvedOptions &o, cudaStream_t user_stream)
 {
     cudaStream_t st = user_stream ? user_stream : c.stream;
-    cudaStream_t st_hey = user_stream ? user_stream : c.stream_hey;
+    // Heyvaerts always runs on the library's second stream, forked from and joined back
+    // into `st` with events, so a caller-supplied stream keeps its ordering semantics.
+    cudaStream_t st_hey = c.stream_hey;
     unsigned long long *counters = static_cast<unsigned long long *>(c.counters.ptr);
     const bool faithful = (o.mode == RIMPHONY_B200_MODE_FAITHFUL);
     const bool want_sym = (o.coeff_mask & 0x3Fu) != 0;

@@ -54,5 +54,6 @@ def golden():
 
 @pytest.fixture(scope="session")
 def symphony_rows():
-    """The reference's golden file tests/symphony-powerlaw.txt (200 x [s, theta, p, J_I, A_I, J_Q, A_Q, J_V, A_V])."""
-    return np.loadtxt(os.path.join(GOLDEN, "symphony-powerlaw.txt"))
+    """The reference's golden vectors tests/symphony-powerlaw.txt (200 x [s, theta, p, J_I, A_I, J_Q, A_Q,
+    J_V, A_V], computed with Symphony), stored as a binary table by tests/golden/make_golden.py."""
+    return np.load(os.path.join(GOLDEN, "symphony_golden.npz"))["table"]

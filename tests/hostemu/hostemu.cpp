@@ -13,6 +13,7 @@
 
 #include "../../rimphony_b200/csrc/rb_symphony.cuh"
 #include "../../rimphony_b200/csrc/rb_heyvaerts.cuh"
+#include "../../rimphony_b200/csrc/rb_symfast.cuh"
 
 using namespace rb;
 
@@ -70,6 +71,21 @@ static void run_symphony(const Dist &d, double s, double theta, const double *ep
     delete ws;
 }
 
+template <int KIND>
+static void run_symphony_fast(const Dist &d, double s, double theta, const double *eps, double *out6, double *lobes4, unsigned *info)
+{
+    auto *ws = new SymFastWS();
+    Warp w;
+    w.init();
+    double o6[6], l4[4];
+    symphony_point_fast<KIND>(w, d, s, theta, eps[0], eps[1], *ws, o6, l4);
+    memcpy(out6, o6, sizeof(o6));
+    memcpy(lobes4, l4, sizeof(l4));
+    info[0] = w.n_apply_lanes;
+    info[1] = w.status;
+    delete ws;
+}
+
 template <int KIND, bool FUSED>
 static void run_heyvaerts(const Dist &d, double s, double theta, const double *eps, double *out2, unsigned *info)
 {
@@ -98,7 +114,9 @@ static int point_kind(const double *params, int n_params, int fused, int which, 
     for (int c = 0; c < 8; c++)
         out8[c] = NAN;
     if (which & 1) {
-        if (fused)
+        if (fused == 2)
+            run_symphony_fast<KIND>(d, s, theta, eps, out8, lobes4, info);
+        else if (fused)
             run_symphony<KIND, true>(d, s, theta, eps, out8, lobes4, info);
         else
             run_symphony<KIND, false>(d, s, theta, eps, out8, lobes4, info);
