@@ -65,21 +65,34 @@ enum {
 };
 
 /* Evaluation modes.
- *   FUSED     product default.  The six j/alpha integrands share every
- *             quadrature node (one J_n / J_{n+1} pair per node) and are converged
- *             together; rho_Q and rho_V likewise, except for points with
- *             s sin(theta) < 3 where the reference's result depends on its exact
- *             sequence of rule applications and the faithful sequence is used.
+ *   FAST      product default.  Same integrands, domains and truncation rules as the
+ *             reference, evaluated by the compact warp engine: the six j/alpha
+ *             integrands share every node, the gamma integral is seeded on the
+ *             J_n^2 peak and cut at the reference Bessel evaluator's region
+ *             boundaries, the harmonic integral marches in ln n.  Agrees with the
+ *             reference's algorithm within its own integration tolerance (1e-3).
  *   FAITHFUL  every coefficient is integrated on its own with the same sequence
- *             of Gauss-Kronrod applications as the reference performs (~6x the
- *             work); agrees with the reference's algorithm to rounding.
+ *             of Gauss-Kronrod applications as the reference performs; agrees with
+ *             the reference's algorithm to rounding.  The parity anchor; slow.
+ *   FUSED     the reference's control flow (QUADPACK bisection, chunked n
+ *             integration with derivative probes) with the six j/alpha integrands,
+ *             and rho_Q / rho_V, converged together on shared nodes; points with
+ *             s sin(theta) < 3 take the faithful Faraday sequence.
  *   FUSED_ALL FUSED without the s sin(theta) < 3 exception (experiments). */
-enum rimphony_b200_mode { RIMPHONY_B200_MODE_FUSED = 0, RIMPHONY_B200_MODE_FAITHFUL = 1, RIMPHONY_B200_MODE_FUSED_ALL = 2 };
+enum rimphony_b200_mode {
+    RIMPHONY_B200_MODE_FAST = 0,
+    RIMPHONY_B200_MODE_FAITHFUL = 1,
+    RIMPHONY_B200_MODE_FUSED_ALL = 2,
+    RIMPHONY_B200_MODE_FUSED = 3
+};
 
 /* Per-point status bits. */
 #define RIMPHONY_B200_STATUS_NAN 1u         /* at least one requested coefficient is NaN */
 #define RIMPHONY_B200_STATUS_CAP_HIT 2u     /* an interval list or step budget filled up */
 #define RIMPHONY_B200_STATUS_NORM_FAILED 4u /* the normalisation integral failed */
+#define RIMPHONY_B200_STATUS_REROUTED 8u    /* FAST mode handed the point to the FAITHFUL sequence: its reference
+                                               value is set by where the reference's quadrature loses the J_n^2
+                                               peak (n > 1e10, hard spectra), see DESIGN.md */
 
 typedef struct rimphony_b200_options {
     uint32_t struct_size;          /* sizeof(rimphony_b200_options); 0-initialise the rest for defaults */

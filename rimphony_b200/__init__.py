@@ -40,9 +40,9 @@ ELECTRON_CHARGE = 4.80320680e-10
 
 POWER_LAW, THERMAL_JUETTNER, PITCHY_PL, PITCHY_KAPPA = 0, 1, 2, 3
 
-MODE_FUSED, MODE_FAITHFUL, MODE_FUSED_ALL = 0, 1, 2
+MODE_FAST, MODE_FAITHFUL, MODE_FUSED_ALL, MODE_FUSED = 0, 1, 2, 3
 
-STATUS_NAN, STATUS_CAP_HIT, STATUS_NORM_FAILED = 1, 2, 4
+STATUS_NAN, STATUS_CAP_HIT, STATUS_NORM_FAILED, STATUS_REROUTED = 1, 2, 4, 8
 
 COEFFICIENT_NAMES = ("j_I", "alpha_I", "j_Q", "alpha_Q", "j_V", "alpha_V", "rho_Q", "rho_V")
 
@@ -78,7 +78,7 @@ def _as_column(x, n):
     return np.ascontiguousarray(a), False
 
 
-def make_options(mode=MODE_FUSED, coeff_mask=0xFF, broadcast_mask=0, device=-1, epsrel_gamma=0.0,
+def make_options(mode=MODE_FAST, coeff_mask=0xFF, broadcast_mask=0, device=-1, epsrel_gamma=0.0,
                  epsrel_n=0.0, epsrel_heyvaerts_inner=0.0, epsrel_heyvaerts_outer=0.0):
     o = _lib.Options()
     o.struct_size = ctypes.sizeof(_lib.Options)
@@ -114,7 +114,7 @@ class BatchResult:
         return np.ascontiguousarray(self.values.T)
 
 
-def compute_all_dimensionless_batch(kind, s, theta, params, *, mode=MODE_FUSED, coeff_mask=0xFF, device=-1,
+def compute_all_dimensionless_batch(kind, s, theta, params, *, mode=MODE_FAST, coeff_mask=0xFF, device=-1,
                                     extras=False, n_devices=None, **tolerances):
     """All eight dimensionless coefficients for ``n`` independent points (host arrays).
 
@@ -164,7 +164,7 @@ def compute_all_dimensionless_batch(kind, s, theta, params, *, mode=MODE_FUSED, 
     return BatchResult(out, status, lobes, counters, norm, last_kernel_ms(device))
 
 
-def compute_all_dimensionless_device(kind, s, theta, params, out8, status=None, *, mode=MODE_FUSED, coeff_mask=0xFF,
+def compute_all_dimensionless_device(kind, s, theta, params, out8, status=None, *, mode=MODE_FAST, coeff_mask=0xFF,
                                      stream=None, synchronize=True, **tolerances):
     """Device-resident variant: every argument is a CUDA ``torch.Tensor`` (float64,
     contiguous; ``status`` int32) already in HBM on the current device; nothing is
@@ -285,7 +285,7 @@ class FullSynchrotronCalculator(SynchrotronCalculator):
     point: ``[n]`` or ``[n, 8]``.
     """
 
-    def __init__(self, distrib, logger=None, mode=MODE_FUSED, device=-1):
+    def __init__(self, distrib, logger=None, mode=MODE_FAST, device=-1):
         self.distrib = distrib
         self.logger = logger
         self.mode = mode
@@ -338,7 +338,7 @@ class _Distribution:
                 return len(c)
         return 1
 
-    def full_calculation(self, logger=None, mode=MODE_FUSED, device=-1):
+    def full_calculation(self, logger=None, mode=MODE_FAST, device=-1):
         """Consumes the parameters and returns the calculator.  The normalisation
         integral the reference computes here (e.g. power_law.rs:93-103) runs on the
         device at the start of every batched call, once per point."""

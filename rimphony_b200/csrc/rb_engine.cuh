@@ -100,6 +100,48 @@ RB_TABLE double LANE_WD[32] = {
     0.025460847326715320186874001019653,  0.015007947329316122538374763075807 - 0.030753241996117268354628393577204,
     0.005377479872923348987792051430128,  0.0};
 
+// The 15-point Kronrod extension of the 7-point Gauss rule (QUADPACK qk15), for the
+// outer quadrature level, whose nodes are visited one after the other: node, Kronrod
+// weight and Kronrod-minus-Gauss weight.
+RB_TABLE double GK15_X[15] = {
+    -0.991455371120812639206854697526329, -0.949107912342758524526189684047851,
+    -0.864864423359769072789712788640926, -0.741531185599394439863864773280788,
+    -0.586087235467691130294144838258730, -0.405845151377397166906606412076961,
+    -0.207784955007898467600689403773245, 0.0,
+    0.207784955007898467600689403773245,  0.405845151377397166906606412076961,
+    0.586087235467691130294144838258730,  0.741531185599394439863864773280788,
+    0.864864423359769072789712788640926,  0.949107912342758524526189684047851,
+    0.991455371120812639206854697526329};
+RB_TABLE double GK15_WK[15] = {
+    0.022935322010529224963732008058970, 0.063092092629978553290700663189204,
+    0.104790010322250183839876322541518, 0.140653259715525918745189590510238,
+    0.169004726639267902826583426598550, 0.190350578064785409913256402421014,
+    0.204432940075298892414161999234649, 0.209482141084727828012999174891714,
+    0.204432940075298892414161999234649, 0.190350578064785409913256402421014,
+    0.169004726639267902826583426598550, 0.140653259715525918745189590510238,
+    0.104790010322250183839876322541518, 0.063092092629978553290700663189204,
+    0.022935322010529224963732008058970};
+RB_TABLE double GK15_WD[15] = {
+    0.022935322010529224963732008058970, 0.063092092629978553290700663189204 - 0.129484966168869693270611432679082,
+    0.104790010322250183839876322541518, 0.140653259715525918745189590510238 - 0.279705391489276667901467771423780,
+    0.169004726639267902826583426598550, 0.190350578064785409913256402421014 - 0.381830050505118944950369775488975,
+    0.204432940075298892414161999234649, 0.209482141084727828012999174891714 - 0.417959183673469387755102040816327,
+    0.204432940075298892414161999234649, 0.190350578064785409913256402421014 - 0.381830050505118944950369775488975,
+    0.169004726639267902826583426598550, 0.140653259715525918745189590510238 - 0.279705391489276667901467771423780,
+    0.104790010322250183839876322541518, 0.063092092629978553290700663189204 - 0.129484966168869693270611432679082,
+    0.022935322010529224963732008058970};
+
+// The 7-point Kronrod extension of the 3-point Gauss rule, for narrow outer panels.
+RB_TABLE double GK7_X[7] = {-0.9604912687080202834235071, -0.7745966692414833770358531, -0.4342437493468025580020715, 0.0,
+                            0.4342437493468025580020715,  0.7745966692414833770358531,  0.9604912687080202834235071};
+RB_TABLE double GK7_WK[7] = {0.1046562260264672651938239, 0.2684880898683334407285693, 0.4013974147759622229050518,
+                             0.4509165386584741423451101, 0.4013974147759622229050518, 0.2684880898683334407285693,
+                             0.1046562260264672651938239};
+RB_TABLE double GK7_WD[7] = {0.1046562260264672651938239, 0.2684880898683334407285693 - 0.5555555555555555555555556,
+                             0.4013974147759622229050518, 0.4509165386584741423451101 - 0.8888888888888888888888889,
+                             0.4013974147759622229050518, 0.2684880898683334407285693 - 0.5555555555555555555555556,
+                             0.1046562260264672651938239};
+
 RB_FN int tile_col(int node) { return node + (node >> 3); }
 
 // Store the node values of one lane (node = lane) into a tile, pre-weighted.

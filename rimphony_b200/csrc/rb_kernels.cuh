@@ -47,8 +47,12 @@ __global__ void __launch_bounds__(kThreadsPerBlock, FUSED ? 3 : 4) k_symphony(Ba
     w.init();
 
     for (;;) {
-        const long long i = next_point(a.next, w.lane);
-        if (i >= a.n)
+        long long i = next_point(a.next, w.lane);
+        if (a.from_reroute_list) {
+            if (i >= (long long)*a.reroute_count)
+                break;
+            i = a.reroute_list[i];
+        } else if (i >= a.n)
             break;
         w.status = 0;
         w.n_apply_lanes = 0;
@@ -61,6 +65,67 @@ __global__ void __launch_bounds__(kThreadsPerBlock, FUSED ? 3 : 4) k_symphony(Ba
         double out6[6], lobes4[4];
         symphony_point<KIND, FUSED, kSymGammaCap, kSymNCap>(w, d, a.s[i], a.theta[i], a.eps_gamma, a.eps_n, ws, out6,
                                                             lobes4);
+
+        if (w.lane == 0) {
+            bool any_nan = false;
+#pragma unroll
+            for (int c = 0; c < 6; c++) {
+                if ((a.coeff_mask >> c) & 1u) {
+                    a.out8[(long long)c * a.n + i] = out6[c];
+                    any_nan |= !(out6[c] == out6[c]);
+                }
+            }
+            if (a.lobes4) {
+#pragma unroll
+                for (int c = 0; c < 4; c++)
+                    a.lobes4[(long long)c * a.n + i] = lobes4[c];
+            }
+            if (a.counters)
+                a.counters[i] = w.n_apply_lanes + (a.from_reroute_list ? a.counters[i] : 0u);
+            const unsigned st = w.status | (any_nan ? kStatusNaN : 0u);
+            if (a.status && st)
+                atomicOr(&a.status[i], (int)st);
+        }
+    }
+}
+
+// The product path: compact engine (rb_engine.cuh, rb_symfast.cuh).
+template <int KIND>
+__global__ void __launch_bounds__(kThreadsPerBlock, 4) k_symphony_fast(BatchArgs a)
+{
+    extern __shared__ double smem[];
+    const int warp = threadIdx.x >> 5;
+    SymFastWS &ws = reinterpret_cast<SymFastWS *>(smem)[warp];
+    Warp w;
+    w.init();
+
+    for (;;) {
+        const long long i = next_point(a.next, w.lane);
+        if (i >= a.n)
+            break;
+        w.status = 0;
+        w.n_apply_lanes = 0;
+
+        Dist d;
+        double p0;
+        load_dist<KIND>(a, i, d, p0);
+        d.norm = a.norm[i];
+
+        double out6[6], lobes4[4];
+        symphony_point_fast<KIND>(w, d, a.s[i], a.theta[i], a.eps_gamma, a.eps_n, ws, out6, lobes4);
+
+        if (w.status & kStatusRerouted) {
+            // fidelity guard (rb_symfast.cuh): the faithful kernel computes this point
+            if (w.lane == 0) {
+                const unsigned long long slot = atomicAdd(a.reroute_count, 1ULL);
+                a.reroute_list[slot] = (int)i;
+                if (a.counters)
+                    a.counters[i] = w.n_apply_lanes;
+                if (a.status)
+                    atomicOr(&a.status[i], (int)kStatusRerouted);
+            }
+            continue;
+        }
 
         if (w.lane == 0) {
             bool any_nan = false;
@@ -181,6 +246,19 @@ int stage_symphony(const BatchArgs &a, bool faithful, int sm_count, cudaStream_t
             return 1;
         k_symphony<KIND, true><<<grid, kThreadsPerBlock, smem, st>>>(a);
     }
+    g_launches++;
+    RB_CUDA(cudaGetLastError());
+    return 0;
+}
+
+template <int KIND>
+int stage_symphony_fast(const BatchArgs &a, int sm_count, cudaStream_t st)
+{
+    int grid = 0;
+    const size_t smem = kWarpsPerBlock * sizeof(SymFastWS);
+    if (set_smem(k_symphony_fast<KIND>, smem) || persistent_grid(k_symphony_fast<KIND>, smem, sm_count, &grid))
+        return 1;
+    k_symphony_fast<KIND><<<grid, kThreadsPerBlock, smem, st>>>(a);
     g_launches++;
     RB_CUDA(cudaGetLastError());
     return 0;

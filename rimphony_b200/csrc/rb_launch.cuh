@@ -11,6 +11,7 @@
 #include <string>
 
 #include "rb_heyvaerts.cuh"
+#include "rb_symfast.cuh"
 #include "rb_symphony.cuh"
 
 namespace rbhost {
@@ -47,6 +48,12 @@ struct BatchArgs {
     unsigned coeff_mask;
     double eps_gamma, eps_n, eps_hey_inner, eps_hey_outer;
     double sigma0_lo, sigma0_hi; // Heyvaerts: only points with sigma0 in [lo, hi)
+    // Symphony fidelity guard: the product kernel appends the points it will not compute to
+    // `reroute_list` (length in reroute_count[0]); the faithful kernel launched after it
+    // takes its points from that list instead of from 0..n-1.
+    int *reroute_list;
+    unsigned long long *reroute_count;
+    int from_reroute_list;
 };
 
 __device__ __forceinline__ long long next_point(unsigned long long *counter, int lane)
@@ -105,6 +112,8 @@ template <int KIND>
 int stage_normalize(const BatchArgs &a, int sm_count, cudaStream_t st);
 template <int KIND>
 int stage_symphony(const BatchArgs &a, bool faithful, int sm_count, cudaStream_t st);
+template <int KIND>
+int stage_symphony_fast(const BatchArgs &a, int sm_count, cudaStream_t st);
 template <int KIND>
 int stage_heyvaerts(const BatchArgs &a, bool fused, int sm_count, cudaStream_t st);
 template <int KIND>

@@ -29,9 +29,24 @@
 namespace rb {
 
 constexpr double kPeakSpan = 3.2;    // seed half-width in units of n^(-1/3)
-constexpr double kInnerFloor = 0.125; // acceptance floor of a gamma panel, fraction of the integral so far
+constexpr double kInnerFloor = 1.0; // acceptance floor of a gamma panel, fraction of the integral so far
 constexpr double kPanelWidth = 2.302585092994046; // outer panel width in u = ln n (one decade)
-constexpr int kMaxPanels = 64;
+constexpr int kMaxChunks = 400;   // safety net of the chunk loop (the reference has none)
+
+// Reference-fidelity guard.  Above n ~ 1e10 the J_n^2 peak (half-width n^(-1/3) of the gamma
+// range) falls between the nodes of the reference's GK31 bisection from the full [gamma_-,
+// gamma_+] and its gamma integral collapses to ~0 (for s < 1e6; above that the reference
+// shrinks the window, symphony.rs:337-341).  A point whose chunks starting beyond
+// kSensitiveN still contribute more than kSensitiveFraction of a coefficient therefore has
+// a reference value that is set by that quadrature failure, not by the integral.  Such
+// points (hard kappa spectra) are not computed here: they are flagged and re-run with the
+// reference's exact sequence of rule applications (MODE_FAITHFUL kernel).
+constexpr double kSensitiveN = 5e9;
+constexpr double kSensitiveFraction = 2e-4;
+constexpr double kTailSkipSpan = 0.25; // outer remainders of the gamma range are dropped below this span
+constexpr bool kCutAtBlendEnd = true;  // also cut the central panels where the blend meets Meissel
+
+constexpr double kNarrowPanel = 0.75; // outer panels narrower than this in u use the 7-point rule
 
 struct SymFastWS {
     EngLevel inner, outer;
@@ -49,10 +64,12 @@ struct SymFastCtx {
 
 // J_n(x) for the argument range of the Symphony integrand (0 <= x <= n): the
 // Debye and Meissel expansions appear once each (pkgw_bessel_j, bessel.c:318-357).
+RB_FN_NOINLINE double leung_j_general(const LeungOrder &o, double x) { return leung_j(o, x); }
+
 RB_FN double leung_j_below(const LeungOrder &o, double x)
 {
     if (o.kind != kOrderLeung || !(x <= o.n))
-        return leung_j(o, x);
+        return leung_j_general(o, x); // integer orders below 30, or x > n: out of line
     const double eps = (o.n - x) / o.n;
     const bool use_debye = !(eps > o.hi_minus);
     const bool use_meissel = !(eps < o.lo_minus) && x != o.n;
@@ -69,17 +86,17 @@ RB_FN double leung_j_below(const LeungOrder &o, double x)
     return use_debye ? dv : mv;
 }
 
-// The six gamma integrands at one node (symphony.rs:398-479).
+// Kinematics of one (n, gamma) node: beta, cos/sin of the pitch angle xi fixed by the
+// resonance condition, and the Bessel argument z with gamma sin(xi) stabilised against
+// cancellation at large gamma, n (symphony.rs:406-439).
 template <int KIND>
-RB_FN void sym_node(const SymFastCtx<KIND> &cx, double n, double gamma, double (&out)[6])
+RB_FN double sym_bessel_arg(const SymFastCtx<KIND> &cx, double n, double gamma, double &beta, double &cos_xi,
+                            double &sin_xi)
 {
     const double s = cx.s, costh = cx.cos_th, sinth = cx.sin_th;
-    const double beta = sqrt(1.0 - 1.0 / (gamma * gamma));
-    const double cos_xi = (s * gamma - n) / (s * gamma * beta * costh);
-    const double sin_xi = sqrt(1.0 - cos_xi * cos_xi);
-    const double m = (costh - beta * cos_xi) / sinth;
-    const double big_n = beta * sin_xi;
-
+    beta = sqrt(1.0 - 1.0 / (gamma * gamma));
+    cos_xi = (s * gamma - n) / (s * gamma * beta * costh);
+    sin_xi = sqrt(1.0 - cos_xi * cos_xi);
     double gamma_sin_xi;
     if (beta < 0.1) {
         gamma_sin_xi = gamma * sin_xi;
@@ -90,7 +107,18 @@ RB_FN void sym_node(const SymFastCtx<KIND> &cx, double n, double gamma, double (
         const double r = 1.0 - 1.0 / beta2_costh2;
         gamma_sin_xi = sqrt(r * (gamma * (gamma + s_on_r)) - (n * n / (s * s * beta2_costh2)));
     }
-    const double z = s * beta * sinth * gamma_sin_xi;
+    return s * beta * sinth * gamma_sin_xi;
+}
+
+// The six gamma integrands at one node (symphony.rs:398-479).
+template <int KIND>
+RB_FN void sym_node(const SymFastCtx<KIND> &cx, double n, double gamma, double (&out)[6])
+{
+    const double costh = cx.cos_th, sinth = cx.sin_th;
+    double beta, cos_xi, sin_xi;
+    const double z = sym_bessel_arg<KIND>(cx, n, gamma, beta, cos_xi, sin_xi);
+    const double m = (costh - beta * cos_xi) / sinth;
+    const double big_n = beta * sin_xi;
 
     // J_n(z), J_{n+1}(z): one copy of the evaluator, two trips
     double jv[2];
@@ -154,18 +182,80 @@ RB_FN_NOINLINE void sym_gamma_integral(Warp &w, const SymFastCtx<KIND> &cx, doub
         leung_prepare(n + 1.0, ws.on1);
     }
 
-    // seeds, pushed so that the two central panels are popped first
+    // Seeds.  Central panels [0, +-T] first (they are popped last-in first-out), outer
+    // remainders after them.  The reference's J_n switches from the Debye expansion to a
+    // blend to Meissel's expansion where eps = (n - z)/n crosses lo_minus and hi_minus
+    // (bessel.c:341-357); the integrand has slope breaks there, so the central panels are
+    // cut at those two values of t (found by a secant solve on the exact eps(t)): every
+    // seed is then smooth and is usually accepted at its first application.
     PanelStack stk;
     stk.reset(&ws.inner);
-    const double span = kPeakSpan * exp(-(1.0 / 3.0) * log(n)) / rel_width;
-    if (span < 0.5) {
+    const double w_peak = exp(-(1.0 / 3.0) * log(n));
+    double span = kPeakSpan * w_peak / rel_width;
+    const bool full = !(span < 0.5);
+    if (full)
+        span = 1.0;
+    else if (!(span < kTailSkipSpan)) {
+        // Beyond |t| = T the Bessel factor is below exp(-(2/3) kPeakSpan^3) of its peak while f
+        // grows at most like (1 - |t|)^-(p+2); the remainders are integrated only while T is
+        // not yet small (n <~ 2000), as a guard for the mildly relativistic regime.
         stk.push(w, -1.0, -span, 0);
         stk.push(w, span, 1.0, 1);
-        stk.push(w, -span, 0.0, 0);
-        stk.push(w, 0.0, span, 1);
-    } else {
-        stk.push(w, -1.0, 0.0, 0);
-        stk.push(w, 0.0, 1.0, 1);
+    }
+    {
+        double cut[2][2]; // [side][which]: 0 < |cut0| <= |cut1| <= span, or == span when absent
+        const bool leung = n >= kNJn;
+        warp_fence(); // orders prepared by lane 0
+        const double lo = ws.on.lo_minus, hi = ws.on.hi_minus;
+        double b_, c_, s_;
+        const double eps0 = leung ? (n - sym_bessel_arg<KIND>(cx, n, gamma_peak, b_, c_, s_)) / n : 0.0;
+#pragma unroll 1
+        for (int side = 0; side < 2; side++) {
+            const double sgn = side ? 1.0 : -1.0;
+#pragma unroll 1
+            for (int k = 0; k < 2; k++) {
+                const double target = k ? hi : lo;
+                double tcut = span;
+                if (leung && eps0 < target && (k == 0 || kCutAtBlendEnd)) {
+                    // eps(t) ~ eps0 + (t rel_width)^2 / 2; refine on the exact function
+                    double t0 = sqrt(2.0 * (target - eps0)) / rel_width;
+                    if (t0 < span) {
+                        double t1 = 1.05 * t0;
+                        double f0 = (n - sym_bessel_arg<KIND>(cx, n, gamma_peak + half * sgn * t0, b_, c_, s_)) / n - target;
+#pragma unroll 1
+                        for (int it = 0; it < 4; it++) {
+                            if (!(t1 < 1.0))
+                                t1 = 0.5 * (t0 + 1.0);
+                            const double f1 =
+                                (n - sym_bessel_arg<KIND>(cx, n, gamma_peak + half * sgn * t1, b_, c_, s_)) / n - target;
+                            const double den = f1 - f0;
+                            if (den == 0.0 || !(den == den))
+                                break;
+                            const double t2 = t1 - f1 * (t1 - t0) / den;
+                            t0 = t1;
+                            f0 = f1;
+                            t1 = t2;
+                            if (!(t1 > 0.0)) {
+                                t1 = t0;
+                                break;
+                            }
+                        }
+                        if (t1 > 0.0 && t1 < span)
+                            tcut = t1;
+                    }
+                }
+                cut[side][k] = tcut;
+            }
+            if (cut[side][0] > cut[side][1])
+                cut[side][0] = cut[side][1];
+            // panels [0, c0], [c0, c1], [c1, span]; empty ones are skipped
+            const double c0 = cut[side][0], c1 = cut[side][1];
+            if (span > c1)
+                stk.push(w, side ? c1 : -span, side ? span : -c1, side);
+            if (c1 > c0)
+                stk.push(w, side ? c0 : -c1, side ? c1 : -c0, side);
+            stk.push(w, side ? 0.0 : -c0, side ? c0 : 0.0, side);
+        }
     }
     stk.seal();
 
@@ -306,21 +396,72 @@ RB_FN void symphony_point_fast(Warp &w, const Dist &dist, double s, double theta
             sym_gamma_integral<KIND>(w, cx, (double)n, tile_col(col), 1.0, 0.0);
     }
     warp_fence();
-    PerChan<double> ans, unused;
-    tile_reduce(ws.outer.tile, kEngChan, 1.0, ans, unused);
+    PerChan<double> disc, unused;
+    tile_reduce(ws.outer.tile, kEngChan, 1.0, disc, unused);
 
-    // the rest, treating n as continuous (symphony.rs:124-140), in u = ln n
+    // The rest, treating n as continuous (symphony.rs:124-140).  The chunks [n_start,
+    // n_start + delta_n] and the rules that grow delta_n and end the loop are the
+    // reference's (symphony.rs:196-295), because where the loop ends decides how much of a
+    // slowly decaying tail (hard kappa spectra) is included: the result is a truncated
+    // integral and parity means truncating it at the same place.  Each chunk is integrated
+    // in u = ln n with the outer rule; the derivative probe is a central difference.
+    PerChan<double> tail, contrib;
     PerChan<bool> active;
-    RB_FOR_CHAN(c, kEngChan) { active[c] = (ans[c] - ans[c] == 0.0); } // finite so far
-    double u = log(n_start);
+    RB_FOR_CHAN(c, kEngChan)
+    {
+        tail[c] = 0.0;
+        contrib[c] = 0.0;
+        active[c] = (disc[c] - disc[c] == 0.0); // finite so far
+    }
+    double n_lo_chunk = n_start;
+    double delta_n = 1e5, incr_step_factor = 10.0;
+    if (s < 10.0) { // "At low harmonic numbers, step conservatively since every n counts."
+        delta_n = 1.0;
+        incr_step_factor = 2.0;
+    }
+    constexpr double kDerivTol = 1e-5, kDerivStep = 1e-3;
     PanelStack stk;
 
-    for (int panel = 0; panel < kMaxPanels; panel++) {
+    for (int chunk_no = 0; chunk_no < kMaxChunks; chunk_no++) {
+        // d G / d n at the start of the chunk
+        warp_fence();
+        tile_clear(w, ws.outer.tile);
+        warp_fence();
+        {
+            const double dn = kDerivStep * n_lo_chunk;
+            sym_gamma_integral<KIND>(w, cx, n_lo_chunk - dn, tile_col(0), -0.5 / dn, 0.0);
+            sym_gamma_integral<KIND>(w, cx, n_lo_chunk + dn, tile_col(1), 0.5 / dn, 0.0);
+        }
+        warp_fence();
+        PerChan<double> deriv, unused2;
+        tile_reduce(ws.outer.tile, kEngChan, 1.0, deriv, unused2);
+        PerChan<bool> grow_c;
+        RB_FOR_CHAN(c, kEngChan)
+        {
+            grow_c[c] = !active[c] || deriv[c] == 0.0 || (contrib[c] != 0.0 && fabs(deriv[c] / contrib[c]) < kDerivTol);
+        }
+        if (chan_all(grow_c, kEngChan))
+            delta_n *= incr_step_factor;
+        if (delta_n < n_lo_chunk / incr_step_factor)
+            delta_n *= incr_step_factor;
+
+        // the chunk, cut into panels of at most kPanelWidth in u; the rightmost is popped first
+        const double u_lo = log(n_lo_chunk), u_hi = log(n_lo_chunk + delta_n);
+        int n_seed = (int)ceil((u_hi - u_lo) / kPanelWidth);
+        if (n_seed < 1)
+            n_seed = 1;
+        if (n_seed > kEngStack - 2)
+            n_seed = kEngStack - 2;
+        stk.reset(&ws.outer);
+        for (int k = 0; k < n_seed; k++)
+            stk.push(w, u_lo + (u_hi - u_lo) * k / n_seed, (k + 1 == n_seed) ? u_hi : u_lo + (u_hi - u_lo) * (k + 1) / n_seed, 0);
+        stk.seal();
+
         PerChan<double> chunk;
         RB_FOR_CHAN(c, kEngChan) { chunk[c] = 0.0; }
-        stk.reset(&ws.outer);
-        stk.push(w, u, u + kPanelWidth, 0);
-        stk.seal();
+        warp_fence();
+        tile_clear(w, ws.outer.tile);
+        int filled = 0;
 
         while (stk.sp > 0) {
             double ua, ub;
@@ -328,10 +469,21 @@ RB_FN void symphony_point_fast(Warp &w, const Dist &dist, double s, double theta
             stk.pop(ua, ub, tag);
             const double uc = 0.5 * (ua + ub), uhl = 0.5 * (ub - ua);
             warp_fence();
+            // outer rule by panel width: K15 for wide panels, K7 for narrow ones
+            const bool narrow = (ub - ua) < kNarrowPanel;
+            const int n_nodes = narrow ? 7 : 15;
+            const double *rx = narrow ? GK7_X : GK15_X;
+            const double *rwk = narrow ? GK7_WK : GK15_WK;
+            const double *rwd = narrow ? GK7_WD : GK15_WD;
+            if (n_nodes < filled) {
+                tile_clear(w, ws.outer.tile);
+                warp_fence();
+            }
+            filled = n_nodes;
 #pragma unroll 1
-            for (int j = 0; j < 31; j++) {
-                const double n = exp(uc + uhl * LANE_X[j]);
-                sym_gamma_integral<KIND>(w, cx, n, tile_col(j), LANE_WK[j] * n, LANE_WD[j] * n);
+            for (int j = 0; j < n_nodes; j++) {
+                const double n = exp(uc + uhl * rx[j]);
+                sym_gamma_integral<KIND>(w, cx, n, tile_col(j), rwk[j] * n, rwd[j] * n);
             }
             warp_fence();
             PerChan<double> r, e;
@@ -340,11 +492,11 @@ RB_FN void symphony_point_fast(Warp &w, const Dist &dist, double s, double theta
             PerChan<bool> ok;
             RB_FOR_CHAN(c, kEngChan)
             {
-                ok[c] = !active[c] || panel_ok(r[c], e[c], epsrel_n, fabs(ans[c] + chunk[c]));
+                ok[c] = !active[c] || panel_ok(r[c], e[c], epsrel_n, fabs(disc[c] + tail[c] + chunk[c]));
             }
             const bool accept = chan_all(ok, kEngChan);
 #ifdef RB_TRACE_FAST
-            RB_TRACE_FAST(panel, ua, ub, r, e, ok, ans, chunk, w.n_apply_lanes);
+            RB_TRACE_FAST(chunk_no, ua, ub, r, e, ok, tail, chunk, w.n_apply_lanes);
 #endif
             if (accept || !stk.room(2) || panel_too_small(ua, ub)) {
                 if (!accept)
@@ -357,21 +509,41 @@ RB_FN void symphony_point_fast(Warp &w, const Dist &dist, double s, double theta
             }
         }
 
+        if (n_lo_chunk >= kSensitiveN && s < 1e6) {
+            PerChan<bool> calm;
+            RB_FOR_CHAN(c, kEngChan)
+            {
+                calm[c] = !active[c] || !(fabs(chunk[c]) > kSensitiveFraction * fabs(disc[c] + tail[c] + chunk[c]));
+            }
+            if (!chan_all(calm, kEngChan)) {
+                w.status |= kStatusRerouted;
+                break;
+            }
+        }
+
         PerChan<bool> done;
         RB_FOR_CHAN(c, kEngChan)
         {
-            ans[c] += chunk[c];
-            // loop condition of the reference; a NaN contribution also ends it
-            if (!(fabs(chunk[c]) >= fabs(ans[c] / kTolerance)))
-                active[c] = false;
+            if (active[c]) {
+                contrib[c] = chunk[c];
+                tail[c] += chunk[c];
+                // loop condition of the reference (symphony.rs:225); a NaN contribution also ends it
+                if (!(fabs(contrib[c]) >= fabs(tail[c] / kTolerance)))
+                    active[c] = false;
+            }
             done[c] = !active[c];
         }
         if (chan_all(done, kEngChan))
             break;
-        u += kPanelWidth;
-        if (panel == kMaxPanels - 1)
+        n_lo_chunk += delta_n;
+        if (n_lo_chunk > 1e13)
+            incr_step_factor = 1.0;
+        if (chunk_no == kMaxChunks - 1)
             w.status |= kStatusCapHit;
     }
+
+    PerChan<double> ans;
+    RB_FOR_CHAN(c, kEngChan) { ans[c] = disc[c] + tail[c]; }
 
     // dimensional constants outside the integrals (symphony.rs:173-183)
     const double two_pi_e = kTwoPi * kElectronCharge;

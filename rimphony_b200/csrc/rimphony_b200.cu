@@ -120,7 +120,7 @@ struct DeviceContext {
     cudaStream_t stream = nullptr;       // Symphony + copies
     cudaStream_t stream_hey = nullptr;   // Heyvaerts, overlaps the Symphony tail
     cudaEvent_t ev[8] = {};
-    DeviceBuffer in, out, scratch, counters;
+    DeviceBuffer in, out, scratch, counters, reroute;
     float last_ms[4] = {0, 0, 0, 0};
     std::mutex lock;
 };
@@ -167,7 +167,7 @@ struct ResolvedOptions {
 
 ResolvedOptions resolve(const rimphony_b200_options *o)
 {
-    ResolvedOptions r{RIMPHONY_B200_MODE_FUSED, 0xFFu, 0u, -1, 1e-3, 1e-3, 1e-3, 1e-3};
+    ResolvedOptions r{RIMPHONY_B200_MODE_FAST, 0xFFu, 0u, -1, 1e-3, 1e-3, 1e-3, 1e-3};
     if (!o)
         return r;
     rimphony_b200_options tmp;
@@ -229,7 +229,18 @@ int launch_kind(DeviceContext &c, BatchArgs a, const ResolvedOptions &o, cudaStr
     // 2. Symphony
     if (want_sym) {
         a.next = counters + 0;
-        if (stage_symphony<KIND>(a, faithful, c.sm_count, st))
+        if (o.mode == RIMPHONY_B200_MODE_FAST) {
+            a.reroute_count = counters + 3;
+            if (stage_symphony_fast<KIND>(a, c.sm_count, st))
+                return 1;
+            // fidelity guard: the points the product kernel handed over, if any
+            BatchArgs b = a;
+            b.next = counters + 0; // reused: reset between the two kernels
+            RB_CUDA(cudaMemsetAsync(counters + 0, 0, sizeof(unsigned long long), st));
+            b.from_reroute_list = 1;
+            if (stage_symphony<KIND>(b, true, c.sm_count, st))
+                return 1;
+        } else if (stage_symphony<KIND>(a, faithful, c.sm_count, st))
             return 1;
     }
     RB_CUDA(cudaEventRecord(c.ev[2], st));
@@ -237,7 +248,8 @@ int launch_kind(DeviceContext &c, BatchArgs a, const ResolvedOptions &o, cudaStr
     // 3. Heyvaerts (second stream: fills the SMs that the Symphony tail leaves idle)
     RB_CUDA(cudaEventRecord(c.ev[3], st_hey));
     if (want_hey) {
-        const double split = (o.mode == RIMPHONY_B200_MODE_FUSED) ? 3.0 : (faithful ? INFINITY : -INFINITY);
+        const bool split_mode = (o.mode == RIMPHONY_B200_MODE_FUSED || o.mode == RIMPHONY_B200_MODE_FAST);
+        const double split = split_mode ? 3.0 : (faithful ? INFINITY : -INFINITY);
         if (split > -INFINITY) { // the reference's exact sequence for sigma0 < split
             BatchArgs b = a;
             b.next = counters + 1;
@@ -306,9 +318,12 @@ int run_device(int kind, int64_t n, const double *s, const double *theta, const 
     }
     if (c.counters.reserve(4 * sizeof(unsigned long long)))
         return 1;
+    if (c.reroute.reserve((size_t)n * sizeof(int)))
+        return 1;
 
     BatchArgs a;
     memset(&a, 0, sizeof a);
+    a.reroute_list = static_cast<int *>(c.reroute.ptr);
     a.n = n;
     a.s = s;
     a.theta = theta;
@@ -356,7 +371,7 @@ int run_host(int kind, int64_t n, const double *s, const double *theta, const do
     if (!s || !theta || !params || !out8)
         return fail("null array pointer");
     ResolvedOptions o = resolve(opts);
-    if (o.mode < 0 || o.mode > 2)
+    if (o.mode < 0 || o.mode > 3)
         return fail("unknown mode %d", o.mode);
     if (device_override >= 0)
         o.device = device_override;
@@ -480,7 +495,7 @@ int rimphony_b200_compute_all_dimensionless_device(int kind, int64_t n_points, c
     if (!s || !theta || !params || !out8)
         return fail("null array pointer");
     ResolvedOptions o = resolve(opts);
-    if (o.mode < 0 || o.mode > 2)
+    if (o.mode < 0 || o.mode > 3)
         return fail("unknown mode %d", o.mode);
     DeviceContext *cp = nullptr;
     if (get_context(o.device, &cp))
@@ -722,6 +737,7 @@ void rimphony_b200_shutdown(void)
         c.out.release();
         c.scratch.release();
         c.counters.release();
+        c.reroute.release();
         for (auto &e : c.ev)
             cudaEventDestroy(e);
         cudaStreamDestroy(c.stream);

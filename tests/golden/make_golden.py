@@ -35,6 +35,7 @@ FIXTURES = {
     # large-sample statistics for the ">= 99.9 % of points within 1e-3" claim (seed differs
     # from the 400-point fixture through the shard argument)
     "pitchy_pl_4k": ("pitchy_pl", 4096),
+    "pitchy_kappa_2k": ("pitchy_kappa", 2048),
 }
 
 
@@ -61,7 +62,7 @@ def run(name):
         s, theta, params = s[sel], theta[sel], [params[0][sel]]
     else:
         config, n = FIXTURES[name]
-        kind, s, theta, params = synthetic_batch(config, n, seed=SEED, shard=(7 if name.endswith("_4k") else 0))
+        kind, s, theta, params = synthetic_batch(config, n, seed=SEED, shard=(7 if name.endswith("k") else 0))
     n = len(s)
     mask = 0xC0 if name == "juettner_sweep" else 0xFF
     out, lobes = O.batch(kind, s, theta, params, coeff_mask=mask)

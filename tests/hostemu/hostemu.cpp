@@ -84,6 +84,12 @@ static void run_symphony_fast(const Dist &d, double s, double theta, const doubl
     info[0] = w.n_apply_lanes;
     info[1] = w.status;
     delete ws;
+    if (w.status & kStatusRerouted) { // what the launcher does: re-run with the faithful kernel
+        unsigned info2[2];
+        run_symphony<KIND, false>(d, s, theta, eps, out6, lobes4, info2);
+        info[0] += info2[0];
+        info[1] |= info2[1] & 0xffu;
+    }
 }
 
 template <int KIND, bool FUSED>
