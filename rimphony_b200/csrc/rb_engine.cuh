@@ -40,6 +40,8 @@ constexpr int kEngRow = 36;         // padded row length: node j sits at column 
                                     // four quarter rows of four channels hit 16 distinct 8-byte banks
 constexpr int kEngStack = 24;       // pending panels per level
 constexpr int kEngTile = 2 * kEngChan * kEngRow; // doubles per tile (A rows then B rows)
+constexpr unsigned kAppBudget = 150000; // rule applications per point after which every panel is accepted as is
+                                        // (status CAP_HIT): bounds the cost of a point whose integral does not converge
 
 // per-warp shared-memory working set of one quadrature level
 struct EngLevel {
@@ -163,6 +165,18 @@ RB_FN void tile_store(double *tile, const Warp &w, int node, const double (&vals
         tile[c * kEngRow + col] = wk * f;
         tile[(kEngChan + c) * kEngRow + col] = wd * f;
     }
+}
+
+RB_FN void tile_clear(const Warp &w, double *tile)
+{
+#ifdef RB_DEVICE_BUILD
+    for (int i = w.lane; i < kEngTile; i += 32)
+        tile[i] = 0.0;
+#else
+    (void)w;
+    for (int i = 0; i < kEngTile; i++)
+        tile[i] = 0.0;
+#endif
 }
 
 // Reduce a tile: per channel the Kronrod estimate r of the integral over a panel

@@ -1,0 +1,477 @@
+// rb_heyfast.cuh -- rho_Q (Heyvaerts' "h") and rho_V ("f") of one point on the
+// product ("fast") path: the non-resonant (NR) + quasi-resonant (QR) double
+// integrals of src/heyvaerts.rs:60-191 evaluated with the compact engine of
+// rb_engine.cuh.
+//
+// Same integrands (rb_heyvaerts.cuh HeyNRIntegrand / HeyQRIntegrand restate
+// heyvaerts.rs:302-468), same domains, same outward-stepping sequence and
+// termination rule as the reference (heyvaerts.rs:85-185): the result is a
+// truncated integral, so the steps [edge, edge + delta], the rule that grows
+// delta (x5 when |1 / (F'(edge) delta)| > 5) and the stop test |contrib / total|
+// <= 1e-5 are kept.  What differs is the quadrature inside a step:
+//
+//   * h and f share every node (coordinates, df/dsigma, the four I_{+-1/3},
+//     I_{+-2/3} or the J/Y pair) and are converged together;
+//   * the NR inner integral over sigma in [sigma_min, sigma_min^1.5/sqrt(3)] and
+//     every outward step are integrated in the logarithm of the variable (the
+//     integrands are algebraic times a power-law-like df/dsigma: smooth in the
+//     log, a bisection cascade towards the lower end in the variable itself);
+//   * the central NR integral over pomega in [-3 sigma0, 3 sigma0] is cut at 0 and,
+//     for sigma0 < 3, at the edges of the hole |pomega| < sqrt(9 - sigma0^2) where
+//     the NR domain is empty (the integrand has slope breaks there);
+//   * the derivative probe of the step rule is a central difference.
+#pragma once
+
+#include "rb_engine.cuh"
+#include "rb_heyvaerts.cuh"
+
+namespace rb {
+
+constexpr double kHeyInnerFloor = 1.0;
+constexpr double kHeyPanelWidth = 2.0; // widest panel in the log of the variable
+constexpr double kHeyDerivStep = 1e-4; // relative step of the derivative probe
+
+struct HeyFastWS {
+    EngLevel inner, outer;
+};
+
+template <int KIND>
+struct HeyFastCtx {
+    const Dist *d;
+    HeyFastWS *ws;
+    HeyGeometry g;
+    double epsrel_inner, epsrel_outer;
+};
+
+enum { kHeyNR = 0, kHeyQR = 1 };
+// how the outer variable is mapped: v = t, v = exp(t), v = -exp(t), v = v_lo + t^2
+enum { kMapLinear = 0, kMapLog = 1, kMapNegLog = 2, kMapSqrt = 3 };
+
+// One inner integral (both channels) at the outer node `v` (pomega for NR, sigma for
+// QR), multiplied by wa / wb and parked in column `col` of the outer tile.
+template <int KIND>
+RB_FN_NOINLINE void hey_inner_integral(Warp &w, const HeyFastCtx<KIND> &cx, int which, double v, int col, double wa,
+                                       double wb)
+{
+    HeyFastWS &ws = *cx.ws;
+    const HeyGeometry &g = cx.g;
+    PanelStack stk;
+    stk.reset(&ws.inner);
+
+    bool empty = false;
+    if (which == kHeyNR) {
+        // heyvaerts.rs:213-250: sigma in [sigma_min, sigma_min^1.5 / sqrt(3)], in t = ln sigma
+        const double sigma_min = sqrt(v * v + g.sigma0_sq);
+        const double sigma_max = kInverseSqrt3 * sigma_min * sqrt(sigma_min);
+        if (!(sigma_max > sigma_min)) {
+            empty = true;
+        } else {
+            const double t_lo = log(sigma_min), t_hi = log(sigma_max);
+            int n_seed = (int)ceil((t_hi - t_lo) / kHeyPanelWidth);
+            n_seed = n_seed < 1 ? 1 : (n_seed > 8 ? 8 : n_seed);
+            for (int k = n_seed - 1; k >= 0; k--) // the lowest panel (largest values) is popped first
+                stk.push(w, t_lo + (t_hi - t_lo) * k / n_seed, (k + 1 == n_seed) ? t_hi : t_lo + (t_hi - t_lo) * (k + 1) / n_seed, 0);
+        }
+    } else {
+        // heyvaerts.rs:262-296: pomega in [-pomega_max, pomega_max]
+        const double pomega_max_phys = sqrt(kThreeTwoThirds * cbrt(v) * v - g.sigma0_sq);
+        const double pomega_max_qr = sqrt(v * v - g.sigma0_sq);
+        const double pomega_max = fmin(pomega_max_phys, pomega_max_qr);
+        if (!(pomega_max > 0.0) && pomega_max == pomega_max)
+            empty = true;
+        else {
+            // The QR elements switch from the I_{+-1/3}, I_{+-2/3} form to the J/Y form where
+            // g = sqrt(8)/3 (sigma - x)^1.5 / sqrt(x) reaches 10 (heyvaerts.rs:33, 330, 358,
+            // 434): the integrand jumps there.  Find x_g with g(x_g) = 10 (g decreases in x;
+            // safeguarded Newton) and cut the pomega range at +-sqrt(sigma^2 - sigma0^2 - x_g^2).
+            double cut = pomega_max;
+            {
+                const double big_k = kGApproximationCutoff / kSqrt8Over3;
+                double lo = 0.0, hi = v, x = 0.5 * v;
+#pragma unroll 1
+                for (int it = 0; it < 40; it++) {
+                    const double d = v - x;
+                    const double h = d * sqrt(d) - big_k * sqrt(x);
+                    if (h > 0.0)
+                        lo = x;
+                    else
+                        hi = x;
+                    const double dh = -1.5 * sqrt(d) - 0.5 * big_k / sqrt(x);
+                    double xn = x - h / dh;
+                    if (!(xn > lo && xn < hi))
+                        xn = 0.5 * (lo + hi);
+                    if (fabs(xn - x) <= 1e-14 * v) {
+                        x = xn;
+                        break;
+                    }
+                    x = xn;
+                }
+                const double p2 = v * v - g.sigma0_sq - x * x;
+                if (p2 > 0.0) {
+                    const double pg = sqrt(p2);
+                    if (pg < pomega_max)
+                        cut = pg;
+                } else
+                    cut = 0.0; // g >= 10 on the whole range
+            }
+            if (cut > 0.0 && cut < pomega_max) {
+                stk.push(w, -pomega_max, -cut, 0);
+                stk.push(w, cut, pomega_max, 0);
+                stk.push(w, -cut, cut, 0);
+            } else
+                stk.push(w, -pomega_max, pomega_max, 0);
+        }
+    }
+    stk.seal();
+
+    PerChan<double> sum, est, big;
+    RB_FOR_CHAN(c, kEngChan)
+    {
+        sum[c] = 0.0;
+        est[c] = 0.0;
+        big[c] = 0.0;
+    }
+
+    while (!empty && stk.sp > 0) {
+        double ta, tb;
+        int tag;
+        stk.pop(ta, tb, tag);
+        const double tc = 0.5 * (ta + tb), thl = 0.5 * (tb - ta);
+        warp_fence();
+#ifdef RB_DEVICE_BUILD
+        {
+            double vals[2];
+            const double t = tc + thl * w.xk;
+            if (which == kHeyNR) {
+                const double sigma = exp(t);
+                HeyNRIntegrand<KIND, 2> f{cx.d, &g, v, 0};
+                f.eval(sigma, vals);
+                vals[0] *= sigma;
+                vals[1] *= sigma;
+            } else {
+                HeyQRIntegrand<KIND, 2> f{cx.d, &g, v, 0};
+                f.eval(t, vals);
+            }
+            tile_store<2>(ws.inner.tile, w, w.lane, vals);
+        }
+#else
+        for (int l = 0; l < 32; l++) {
+            double vals[2];
+            const double t = tc + thl * LANE_X[l];
+            if (which == kHeyNR) {
+                const double sigma = exp(t);
+                HeyNRIntegrand<KIND, 2> f{cx.d, &g, v, 0};
+                f.eval(sigma, vals);
+                vals[0] *= sigma;
+                vals[1] *= sigma;
+            } else {
+                HeyQRIntegrand<KIND, 2> f{cx.d, &g, v, 0};
+                f.eval(t, vals);
+            }
+            tile_store<2>(ws.inner.tile, w, l, vals);
+        }
+#endif
+        w.n_apply_lanes++;
+        warp_fence();
+
+        PerChan<double> r, e;
+        tile_reduce(ws.inner.tile, 2, thl, r, e);
+
+        PerChan<bool> ok;
+        RB_FOR_CHAN(c, kEngChan) { ok[c] = true; }
+        RB_FOR_CHAN(c, 2)
+        {
+            big[c] = fmax(big[c], fabs(r[c]));
+            ok[c] = panel_ok(r[c], e[c], cx.epsrel_inner, kHeyInnerFloor * fmax(est[c] + fabs(r[c]), big[c]));
+        }
+        const bool accept = chan_all(ok, 2);
+        if (accept || !stk.room(2) || panel_too_small(ta, tb) || w.n_apply_lanes > kAppBudget) {
+            if (!accept)
+                w.status |= kStatusCapHit;
+            RB_FOR_CHAN(c, 2)
+            {
+                est[c] += fabs(r[c]);
+                sum[c] += r[c];
+            }
+        } else {
+            stk.push(w, tc, tb, 0);
+            stk.push(w, ta, tc, 0);
+            stk.seal();
+        }
+    }
+
+    double *ot = ws.outer.tile;
+#ifdef RB_DEVICE_BUILD
+    if ((w.lane & 3) == 0)
+#endif
+    {
+        RB_FOR_CHAN(c, 2)
+        {
+            ot[c * kEngRow + col] = wa * sum[c];
+            ot[(kEngChan + c) * kEngRow + col] = wb * sum[c];
+        }
+    }
+}
+
+// The outer integral of one step: both channels over v in [v_lo, v_hi] (same sign, or any
+// interval for the linear map), adaptive in the mapped variable with the sequential K15 / K7
+// rules.  `scale` is the magnitude of the running total, the floor of the acceptance test.
+template <int KIND>
+RB_FN_NOINLINE void hey_outer_integral(Warp &w, const HeyFastCtx<KIND> &cx, int which, int map, double v_lo, double v_hi,
+                                       const PerChan<double> &scale, PerChan<double> &result)
+{
+    HeyFastWS &ws = *cx.ws;
+    PanelStack stk;
+    stk.reset(&ws.outer);
+
+    // mapped range [t_lo, t_hi]; `offset` is the start of the sqrt map v = offset + t^2
+    double t_lo, t_hi;
+    if (map == kMapLinear) {
+        t_lo = v_lo;
+        t_hi = v_hi;
+    } else if (map == kMapSqrt) {
+        t_lo = 0.0;
+        t_hi = sqrt(v_hi - v_lo);
+    } else {
+        // v = +-exp(t); for the negative branch t runs from ln|v_hi| to ln|v_lo|
+        t_lo = (map == kMapLog) ? log(v_lo) : log(-v_hi);
+        t_hi = (map == kMapLog) ? log(v_hi) : log(-v_lo);
+    }
+    const double offset = v_lo;
+    {
+        // Break point: the NR integrand has a cusp at pomega* = sigma0 cot(theta), where the
+        // lower end of the inner sigma range touches gamma = 1 (there a power law's
+        // 1/(gamma^2 beta) is singular); panels are cut there.
+        double t_star = t_hi;
+        if (which == kHeyNR) {
+            const double p_star = cx.g.sigma0 * cx.g.cos_th / cx.g.sin_th;
+            if (p_star > v_lo && p_star < v_hi)
+                t_star = (map == kMapLinear) ? p_star : log(p_star); // p_star > 0: linear or log map
+        }
+        const double max_w = (map == kMapLog || map == kMapNegLog) ? kHeyPanelWidth : INFINITY;
+        // upper segment [t_star, t_hi] first so that the lower one is popped first
+#pragma unroll 1
+        for (int seg = 1; seg >= 0; seg--) {
+            const double a = seg ? t_star : t_lo, b = seg ? t_hi : t_star;
+            if (!(b > a))
+                continue;
+            int n_seed = (max_w < INFINITY) ? (int)ceil((b - a) / max_w) : 1;
+            n_seed = n_seed < 1 ? 1 : (n_seed > 8 ? 8 : n_seed);
+            for (int k = n_seed - 1; k >= 0; k--)
+                stk.push(w, a + (b - a) * k / n_seed, (k + 1 == n_seed) ? b : a + (b - a) * (k + 1) / n_seed, 0);
+        }
+    }
+    stk.seal();
+
+    PerChan<double> big; // largest |panel value| seen in this step, accepted or not
+    RB_FOR_CHAN(c, kEngChan)
+    {
+        result[c] = 0.0;
+        big[c] = 0.0;
+    }
+    warp_fence();
+    tile_clear(w, ws.outer.tile);
+    int filled = 0;
+
+    while (stk.sp > 0) {
+        double ta, tb;
+        int tag;
+        stk.pop(ta, tb, tag);
+        const double tc = 0.5 * (ta + tb), thl = 0.5 * (tb - ta);
+        warp_fence();
+        const bool narrow = (map == kMapLog || map == kMapNegLog) && (tb - ta) < 0.75;
+        const int n_nodes = narrow ? 7 : 15;
+        const double *rx = narrow ? GK7_X : GK15_X;
+        const double *rwk = narrow ? GK7_WK : GK15_WK;
+        const double *rwd = narrow ? GK7_WD : GK15_WD;
+        if (n_nodes < filled) {
+            tile_clear(w, ws.outer.tile);
+            warp_fence();
+        }
+        filled = n_nodes;
+#pragma unroll 1
+        for (int j = 0; j < n_nodes; j++) {
+            const double t = tc + thl * rx[j];
+            double v = t, jac = 1.0;
+            if (map == kMapSqrt) {
+                v = offset + t * t;
+                jac = 2.0 * t;
+            } else if (map != kMapLinear) {
+                jac = exp(t);
+                v = (map == kMapLog) ? jac : -jac;
+            }
+            hey_inner_integral<KIND>(w, cx, which, v, tile_col(j), rwk[j] * jac, rwd[j] * jac);
+        }
+        warp_fence();
+        PerChan<double> r, e;
+        tile_reduce(ws.outer.tile, 2, thl, r, e);
+
+        PerChan<bool> ok;
+        RB_FOR_CHAN(c, kEngChan) { ok[c] = true; }
+        RB_FOR_CHAN(c, 2)
+        {
+            big[c] = fmax(big[c], fabs(r[c]));
+            ok[c] = panel_ok(r[c], e[c], cx.epsrel_outer, fmax(fabs(scale[c]) + fabs(result[c]), big[c]));
+        }
+        const bool accept = chan_all(ok, 2);
+#ifdef RB_TRACE_HEYFAST
+        RB_TRACE_HEYFAST(which, map, ta, tb, r, e, ok, w.n_apply_lanes);
+#endif
+        if (accept || !stk.room(2) || panel_too_small(ta, tb) || w.n_apply_lanes > kAppBudget) {
+            if (!accept)
+                w.status |= kStatusCapHit;
+            RB_FOR_CHAN(c, 2) { result[c] += r[c]; }
+        } else {
+            stk.push(w, tc, tb, 0);
+            stk.push(w, ta, tc, 0);
+            stk.seal();
+        }
+    }
+}
+
+// d F / d v of the outer integrand at `v` (both channels), by a central difference.
+template <int KIND>
+RB_FN void hey_outer_derivative(Warp &w, const HeyFastCtx<KIND> &cx, int which, double v, PerChan<double> &deriv)
+{
+    HeyFastWS &ws = *cx.ws;
+    warp_fence();
+    tile_clear(w, ws.outer.tile);
+    warp_fence();
+    const double dv = kHeyDerivStep * fabs(v);
+    hey_inner_integral<KIND>(w, cx, which, v - dv, tile_col(0), -0.5 / dv, 0.0);
+    hey_inner_integral<KIND>(w, cx, which, v + dv, tile_col(1), 0.5 / dv, 0.0);
+    warp_fence();
+    PerChan<double> unused;
+    tile_reduce(ws.outer.tile, 2, 1.0, deriv, unused);
+}
+
+// One outward-stepping stage of heyvaerts.rs:102-185 (cf. hey_step_outward<> in
+// rb_heyvaerts.cuh, whose bookkeeping this follows with per-lane channel state).
+template <int KIND>
+RB_FN_NOINLINE void hey_march(Warp &w, const HeyFastCtx<KIND> &cx, int which, double edge, double delta, int dir,
+                              bool skip_while_zero, double delta_cap, PerChan<double> &val, PerChan<bool> &alive)
+{
+    constexpr double kTol = 1e-5, kDeltaScale = 5.0;
+    PerChan<bool> keep;
+    RB_FOR_CHAN(c, kEngChan) { keep[c] = false; }
+    RB_FOR_CHAN(c, 2) { keep[c] = alive[c]; }
+
+    for (int steps = 0;; steps++) {
+        PerChan<bool> idle;
+        RB_FOR_CHAN(c, kEngChan) { idle[c] = !keep[c]; }
+        if (chan_all(idle, kEngChan))
+            break;
+        if (steps >= kHeyMaxSteps) {
+            w.status |= kStatusCapHit;
+            break;
+        }
+
+        // the step-size rule is voted by the channels that take part in it
+        PerChan<bool> voter, none;
+        RB_FOR_CHAN(c, kEngChan)
+        {
+            voter[c] = keep[c] && !(skip_while_zero && val[c] == 0.0);
+            none[c] = !voter[c];
+        }
+        if (!chan_all(none, kEngChan)) {
+            PerChan<double> deriv;
+            hey_outer_derivative<KIND>(w, cx, which, edge, deriv);
+            PerChan<bool> grow;
+            RB_FOR_CHAN(c, kEngChan)
+            {
+                grow[c] = !voter[c] || deriv[c] == 0.0 || (fabs(1.0 / (deriv[c] * delta)) > kDeltaScale);
+            }
+            if (chan_all(grow, kEngChan) && delta < delta_cap)
+                delta *= kDeltaScale;
+        }
+
+        const double lo = dir > 0 ? edge : edge - delta, hi = dir > 0 ? edge + delta : edge;
+        // the QR outer integrand starts like sqrt(sigma - sigma_low) (pomega_max = 0 there):
+        // the first QR step is integrated in t = sqrt(sigma - sigma_low)
+        const int map = (which == kHeyQR && steps == 0) ? kMapSqrt
+                                                       : ((lo > 0.0) ? kMapLog : ((hi < 0.0) ? kMapNegLog : kMapLinear));
+        PerChan<double> contrib;
+        hey_outer_integral<KIND>(w, cx, which, map, lo, hi, val, contrib);
+
+        RB_FOR_CHAN(c, 2)
+        {
+            if (keep[c]) {
+                if (!(contrib[c] == contrib[c])) { // NaN: the reference returns NaN
+                    val[c] = NAN;
+                    alive[c] = false;
+                    keep[c] = false;
+                } else {
+                    if (!(skip_while_zero && val[c] == 0.0)) {
+                        if (!(fabs(contrib[c] / val[c]) > kTol))
+                            keep[c] = false;
+                    }
+                    val[c] += contrib[c];
+                }
+            }
+        }
+        edge += dir * delta;
+    }
+}
+
+// rho_Q and rho_V of one point, dimensionless (heyvaerts.rs:60-191).
+template <int KIND>
+RB_FN void heyvaerts_point_fast(Warp &w, const Dist &dist, double s, double theta, double epsrel_inner,
+                                double epsrel_outer, HeyFastWS &ws, double (&out2)[2])
+{
+    HeyFastCtx<KIND> cx;
+    cx.d = &dist;
+    cx.ws = &ws;
+    cx.g.cos_th = cos(theta);
+    cx.g.sin_th = sin(theta);
+    cx.g.sigma0 = s * cx.g.sin_th;
+    cx.g.sigma0_sq = cx.g.sigma0 * cx.g.sigma0;
+    cx.epsrel_inner = epsrel_inner;
+    cx.epsrel_outer = epsrel_outer;
+    const double sigma0 = cx.g.sigma0;
+
+    PerChan<bool> alive;
+    PerChan<double> nr_val, qr_val;
+    RB_FOR_CHAN(c, kEngChan)
+    {
+        alive[c] = false;
+        nr_val[c] = 0.0;
+        qr_val[c] = 0.0;
+    }
+    RB_FOR_CHAN(c, 2) { alive[c] = true; }
+
+    // the central NR integral over [-3 sigma0, 3 sigma0] (heyvaerts.rs:97), cut at 0 and at
+    // the edges of the empty region sigma_min <= 3
+    {
+        const double p3 = 3.0 * sigma0;
+        const double hole = (sigma0 < 3.0) ? sqrt(9.0 - cx.g.sigma0_sq) : 0.0;
+        if (p3 > hole) {
+            PerChan<double> part;
+            hey_outer_integral<KIND>(w, cx, kHeyNR, kMapLinear, hole, p3, nr_val, part);
+            RB_FOR_CHAN(c, 2) { nr_val[c] += part[c]; }
+            hey_outer_integral<KIND>(w, cx, kHeyNR, kMapLinear, -p3, -hole, nr_val, part);
+            RB_FOR_CHAN(c, 2) { nr_val[c] += part[c]; }
+        }
+        RB_FOR_CHAN(c, 2)
+        {
+            if (!(nr_val[c] == nr_val[c]))
+                alive[c] = false;
+        }
+    }
+
+    const double p3 = 3.0 * sigma0;
+    hey_march<KIND>(w, cx, kHeyNR, p3, p3, +1, true, INFINITY, nr_val, alive);
+    hey_march<KIND>(w, cx, kHeyNR, -p3, p3, -1, false, INFINITY, nr_val, alive);
+
+    const double s15 = kInverseSqrt3 * sigma0 * sqrt(sigma0);
+    const double sigma_low = sigma0 > s15 ? sigma0 : s15;
+    hey_march<KIND>(w, cx, kHeyQR, sigma_low, sigma0, +1, true, 1e6 * sigma0, qr_val, alive);
+
+    const double scale = 2.0 * kElectronCharge * kElectronCharge / (kMassElectron * (s * cx.g.sin_th) * (s * cx.g.sin_th));
+    PerChan<double> total;
+    RB_FOR_CHAN(c, kEngChan) { total[c] = NAN; }
+    RB_FOR_CHAN(c, 2) { total[c] = alive[c] ? scale * (nr_val[c] + qr_val[c]) : NAN; }
+    out2[0] = chan_get(total, 0);
+    out2[1] = chan_get(total, 1);
+}
+
+} // namespace rb

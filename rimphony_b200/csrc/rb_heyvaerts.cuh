@@ -253,7 +253,13 @@ RB_FN_NOINLINE void hey_step_outward(Warp &w, Outer &F, IntervalList<NV> &olist,
 
         const double bounds[2] = {dir > 0 ? edge : edge - delta, dir > 0 ? edge + delta : edge};
         double contrib[NV];
+#ifdef RB_TRACE_HEY
+        const unsigned apps0_ = w.n_apply_lanes;
+#endif
         qag_joint<PolicyPlain<NV>>(w, ap, 1, bounds, epsrel_outer, olist, keep, contrib);
+#ifdef RB_TRACE_HEY
+        RB_TRACE_HEY("step", bounds[0], bounds[1], contrib, val, w.n_apply_lanes - apps0_, olist.size);
+#endif
 
 #pragma unroll
         for (int c = 0; c < NV; c++) {
@@ -307,6 +313,9 @@ RB_FN void heyvaerts_point(Warp &w, const Dist &dist, double s, double theta, do
             ApplySeq<NV, HeyNROuter<KIND, NV>> ap{nr};
             const double bounds[2] = {-3.0 * geom.sigma0, 3.0 * geom.sigma0};
             qag_joint<PolicyPlain<NV>>(w, ap, 1, bounds, epsrel_outer, olist, all, nr_val);
+#ifdef RB_TRACE_HEY
+            RB_TRACE_HEY("init", bounds[0], bounds[1], nr_val, nr_val, w.n_apply_lanes, olist.size);
+#endif
 #pragma unroll
             for (int c = 0; c < NV; c++)
                 if (!(nr_val[c] == nr_val[c]))

@@ -198,6 +198,49 @@ __global__ void __launch_bounds__(kThreadsPerBlock, 4) k_heyvaerts(BatchArgs a)
     }
 }
 
+// The product path for rho_Q, rho_V: compact engine (rb_engine.cuh, rb_heyfast.cuh).
+template <int KIND>
+__global__ void __launch_bounds__(kThreadsPerBlock, 4) k_heyvaerts_fast(BatchArgs a)
+{
+    extern __shared__ double smem[];
+    const int warp = threadIdx.x >> 5;
+    HeyFastWS &ws = reinterpret_cast<HeyFastWS *>(smem)[warp];
+    Warp w;
+    w.init();
+
+    for (;;) {
+        const long long i = next_point(a.next, w.lane);
+        if (i >= a.n)
+            break;
+        w.status = 0;
+        w.n_apply_lanes = 0;
+
+        Dist d;
+        double p0;
+        load_dist<KIND>(a, i, d, p0);
+        d.norm = a.norm[i];
+
+        double out2[2];
+        heyvaerts_point_fast<KIND>(w, d, a.s[i], a.theta[i], a.eps_hey_inner, a.eps_hey_outer, ws, out2);
+
+        if (w.lane == 0) {
+            bool any_nan = false;
+#pragma unroll
+            for (int c = 0; c < 2; c++) {
+                if ((a.coeff_mask >> (6 + c)) & 1u) {
+                    a.out8[(long long)(6 + c) * a.n + i] = out2[c];
+                    any_nan |= !(out2[c] == out2[c]);
+                }
+            }
+            if (a.counters)
+                a.counters[a.n + i] = w.n_apply_lanes;
+            const unsigned st = w.status | (any_nan ? kStatusNaN : 0u);
+            if (a.status && st)
+                atomicOr(&a.status[i], (int)st);
+        }
+    }
+}
+
 template <int KIND>
 __global__ void k_dist_eval(Dist d, long long count, const double *gamma, const double *cos_xi, double *out3)
 {
@@ -279,6 +322,19 @@ int stage_heyvaerts(const BatchArgs &a, bool fused, int sm_count, cudaStream_t s
             return 1;
         k_heyvaerts<KIND, true><<<grid, kThreadsPerBlock, smem, st>>>(a);
     }
+    g_launches++;
+    RB_CUDA(cudaGetLastError());
+    return 0;
+}
+
+template <int KIND>
+int stage_heyvaerts_fast(const BatchArgs &a, int sm_count, cudaStream_t st)
+{
+    int grid = 0;
+    const size_t smem = kWarpsPerBlock * sizeof(HeyFastWS);
+    if (set_smem(k_heyvaerts_fast<KIND>, smem) || persistent_grid(k_heyvaerts_fast<KIND>, smem, sm_count, &grid))
+        return 1;
+    k_heyvaerts_fast<KIND><<<grid, kThreadsPerBlock, smem, st>>>(a);
     g_launches++;
     RB_CUDA(cudaGetLastError());
     return 0;

@@ -11,6 +11,7 @@
 #include <string>
 
 #include "rb_heyvaerts.cuh"
+#include "rb_heyfast.cuh"
 #include "rb_symfast.cuh"
 #include "rb_symphony.cuh"
 
@@ -116,6 +117,8 @@ template <int KIND>
 int stage_symphony_fast(const BatchArgs &a, int sm_count, cudaStream_t st);
 template <int KIND>
 int stage_heyvaerts(const BatchArgs &a, bool fused, int sm_count, cudaStream_t st);
+template <int KIND>
+int stage_heyvaerts_fast(const BatchArgs &a, int sm_count, cudaStream_t st);
 template <int KIND>
 int stage_dist_eval(const double *params, int n_params, long long count, const double *gamma, const double *cos_xi,
                     double *out3, cudaStream_t st);

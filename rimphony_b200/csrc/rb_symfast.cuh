@@ -307,7 +307,7 @@ RB_FN_NOINLINE void sym_gamma_integral(Warp &w, const SymFastCtx<KIND> &cx, doub
 #ifdef RB_TRACE_INNER
         RB_TRACE_INNER(n, ta, tb, r, e, ok, est);
 #endif
-        if (accept || !stk.room(2) || panel_too_small(ta, tb)) {
+        if (accept || !stk.room(2) || panel_too_small(ta, tb) || w.n_apply_lanes > kAppBudget) {
             if (!accept)
                 w.status |= kStatusCapHit;
             RB_FOR_CHAN(c, 6)
@@ -351,18 +351,6 @@ RB_FN_NOINLINE void sym_gamma_integral(Warp &w, const SymFastCtx<KIND> &cx, doub
             }
         }
     }
-}
-
-RB_FN void tile_clear(const Warp &w, double *tile)
-{
-#ifdef RB_DEVICE_BUILD
-    for (int i = w.lane; i < kEngTile; i += 32)
-        tile[i] = 0.0;
-#else
-    (void)w;
-    for (int i = 0; i < kEngTile; i++)
-        tile[i] = 0.0;
-#endif
 }
 
 // All six j/alpha coefficients of one point, dimensionless (lib.rs:178-191);
@@ -498,7 +486,7 @@ RB_FN void symphony_point_fast(Warp &w, const Dist &dist, double s, double theta
 #ifdef RB_TRACE_FAST
             RB_TRACE_FAST(chunk_no, ua, ub, r, e, ok, tail, chunk, w.n_apply_lanes);
 #endif
-            if (accept || !stk.room(2) || panel_too_small(ua, ub)) {
+            if (accept || !stk.room(2) || panel_too_small(ua, ub) || w.n_apply_lanes > kAppBudget) {
                 if (!accept)
                     w.status |= kStatusCapHit;
                 RB_FOR_CHAN(c, kEngChan) { chunk[c] += r[c]; }

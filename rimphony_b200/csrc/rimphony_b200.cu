@@ -247,8 +247,13 @@ int launch_kind(DeviceContext &c, BatchArgs a, const ResolvedOptions &o, cudaStr
 
     // 3. Heyvaerts (second stream: fills the SMs that the Symphony tail leaves idle)
     RB_CUDA(cudaEventRecord(c.ev[3], st_hey));
-    if (want_hey) {
-        const bool split_mode = (o.mode == RIMPHONY_B200_MODE_FUSED || o.mode == RIMPHONY_B200_MODE_FAST);
+    if (want_hey && o.mode == RIMPHONY_B200_MODE_FAST) {
+        BatchArgs b = a;
+        b.next = counters + 1;
+        if (stage_heyvaerts_fast<KIND>(b, c.sm_count, st_hey))
+            return 1;
+    } else if (want_hey) {
+        const bool split_mode = (o.mode == RIMPHONY_B200_MODE_FUSED);
         const double split = split_mode ? 3.0 : (faithful ? INFINITY : -INFINITY);
         if (split > -INFINITY) { // the reference's exact sequence for sigma0 < split
             BatchArgs b = a;

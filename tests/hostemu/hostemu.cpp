@@ -14,6 +14,7 @@
 #include "../../rimphony_b200/csrc/rb_symphony.cuh"
 #include "../../rimphony_b200/csrc/rb_heyvaerts.cuh"
 #include "../../rimphony_b200/csrc/rb_symfast.cuh"
+#include "../../rimphony_b200/csrc/rb_heyfast.cuh"
 
 using namespace rb;
 
@@ -109,6 +110,21 @@ static void run_heyvaerts(const Dist &d, double s, double theta, const double *e
 }
 
 template <int KIND>
+static void run_heyvaerts_fast(const Dist &d, double s, double theta, const double *eps, double *out2, unsigned *info)
+{
+    auto *ws = new HeyFastWS();
+    Warp w;
+    w.init();
+    double o2[2];
+    heyvaerts_point_fast<KIND>(w, d, s, theta, eps[2], eps[3], *ws, o2);
+    out2[0] = o2[0];
+    out2[1] = o2[1];
+    info[0] = w.n_apply_lanes;
+    info[1] = w.status;
+    delete ws;
+}
+
+template <int KIND>
 static int point_kind(const double *params, int n_params, int fused, int which, double s, double theta,
                       const double *eps, double *out8, double *lobes4, unsigned *info)
 {
@@ -128,7 +144,9 @@ static int point_kind(const double *params, int n_params, int fused, int which, 
             run_symphony<KIND, false>(d, s, theta, eps, out8, lobes4, info);
     }
     if (which & 2) {
-        if (fused)
+        if (fused == 2)
+            run_heyvaerts_fast<KIND>(d, s, theta, eps, out8 + 6, info + 2);
+        else if (fused)
             run_heyvaerts<KIND, true>(d, s, theta, eps, out8 + 6, info + 2);
         else
             run_heyvaerts<KIND, false>(d, s, theta, eps, out8 + 6, info + 2);
