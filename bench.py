@@ -35,9 +35,13 @@ METRIC = "8-coefficient sets/sec"
 UNIT = "coefficient-sets/s"
 SEED = 20260
 
-# FP64 floating-point operations per 31-node Gauss-Kronrod application (FMA = 2),
-# from the ncu instruction counts in profiles/ (see DESIGN.md section 7).
-FLOP_PER_APPLICATION = {"symphony": 31 * 2200.0, "heyvaerts": 31 * 900.0}
+# FP64 floating-point operations executed per 31-node Gauss-Kronrod application (FMA = 2): ncu
+# smsp__sass_thread_inst_executed_op_{dfma,dmul,dadd}_pred_on over one launch of each product
+# kernel divided by the applications that launch counted (profiles/r01_fast_kernels_details.txt,
+# 4096 seeded pitchy power-law points: 2127 / 1037 flop per SM-clock cycle over 48.0 / 231.8 ms).
+FLOP_PER_APPLICATION = {"symphony": 45.7e3, "heyvaerts": 25.3e3}
+# DRAM bytes (read + write) per point of the same captures: the path does not touch HBM.
+DRAM_BYTES_PER_POINT = {"symphony": (324.9e3 + 5.07e6) / 4096, "heyvaerts": (671.5e3 + 2.91e6) / 4096}
 
 
 def parse():
@@ -46,7 +50,8 @@ def parse():
     ap.add_argument("--steps", type=int, default=3)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--points", type=int, default=65536, help="points per GPU per step")
+    ap.add_argument("--points", type=int, default=262144,
+                    help="points per GPU per step (the full BASELINE configs[2] batch is 10000000)")
     ap.add_argument("--config", default="pitchy_pl", choices=["pitchy_pl", "powerlaw", "pitchy_kappa"])
     ap.add_argument("--cpu-sample", type=int, default=0, help="points of the CPU sample (0 = auto, ~20 s)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
@@ -54,8 +59,9 @@ def parse():
 
 
 def workload_name(config, points):
-    return (f"{config} (crank-out shape, BASELINE configs[2] distribution), {points} points per GPU per step, "
-            "all 8 coefficients, mode=fused")
+    return (f"{config} (crank-out-pitchypl shape: BASELINE configs[2] point distribution, seeded), {points} points per "
+            "GPU per step (a slice of the 10 M-point batch; --points 10000000 runs all of it), all 8 coefficients, "
+            "mode=fast")
 
 
 class ClockSampler:
@@ -288,8 +294,10 @@ def main():
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
             "gpu_launches": int(launches),
             "clocks": clocks,
-            "roofline": {"bound": "fp64", "kernel": "k_" + dominant, "achieved": achieved, "peak": peak, "unit": "TFLOP/s",
-                         "frac": achieved / peak if peak else None, "traffic": None,
+            "roofline": {"bound": "fp64", "kernel": "k_" + dominant + "_fast", "achieved": achieved, "peak": peak, "unit": "TFLOP/s",
+                         "frac": achieved / peak if peak else None,
+                         "traffic": DRAM_BYTES_PER_POINT[dominant] * n,
+                         "traffic_note": "bytes per launch, scaled per point from the ncu --set full capture in profiles/",
                          "peak_source": "measured in this run: register-resident DFMA kernel "
                                         "(MEASURED_PEAKS.json has no FP64 figure)",
                          "kernel_ms": {"normalize": k_ms[0], "symphony": k_ms[1], "heyvaerts": k_ms[2], "span": k_ms[3]},
