@@ -47,6 +47,13 @@ enum { kHeyNR = 0, kHeyQR = 1 };
 // how the outer variable is mapped: v = t, v = exp(t), v = -exp(t), v = v_lo + t^2
 enum { kMapLinear = 0, kMapLog = 1, kMapNegLog = 2, kMapSqrt = 3 };
 
+// Note on NaN: at the isolated points of the (sigma, pomega) plane where gamma = 1 a power law's
+// f and its derivatives are infinite and df/dsigma evaluates to inf - inf.  For s sin(theta) < 1
+// deep bisection towards such a point can land a node on it; the NaN then propagates to the
+// coefficient (status NAN), which is also what the reference's QAG does when it happens to it.
+// (Dropping the sample instead makes these points integrate a non-integrable singularity to
+// the application budget: 10x the cost for values nobody can use.)
+
 // One inner integral (both channels) at the outer node `v` (pomega for NR, sigma for
 // QR), multiplied by wa / wb and parked in column `col` of the outer tile.
 template <int KIND>
@@ -59,6 +66,11 @@ RB_FN_NOINLINE void hey_inner_integral(Warp &w, const HeyFastCtx<KIND> &cx, int 
     stk.reset(&ws.inner);
 
     bool empty = false;
+    // QR with pomega_max = sqrt(sigma^2 - sigma0^2): x -> 0 at both ends of the pomega range and the
+    // elements behave like powers of x = sqrt(pomega_max^2 - pomega^2) there; pomega = pomega_max sin(phi)
+    // makes x = pomega_max cos(phi) and the integrand analytic in phi.
+    bool sine_map = false;
+    double sine_amp = 0.0;
     if (which == kHeyNR) {
         // heyvaerts.rs:213-250: sigma in [sigma_min, sigma_min^1.5 / sqrt(3)], in t = ln sigma
         const double sigma_min = sqrt(v * v + g.sigma0_sq);
@@ -114,12 +126,22 @@ RB_FN_NOINLINE void hey_inner_integral(Warp &w, const HeyFastCtx<KIND> &cx, int 
                 } else
                     cut = 0.0; // g >= 10 on the whole range
             }
-            if (cut > 0.0 && cut < pomega_max) {
-                stk.push(w, -pomega_max, -cut, 0);
-                stk.push(w, cut, pomega_max, 0);
+            double end = pomega_max;
+            if (pomega_max_qr <= pomega_max_phys) {
+                sine_map = true;
+                sine_amp = pomega_max;
+                end = 0.5 * kPi;
+                if (cut > 0.0 && cut < pomega_max)
+                    cut = asin(cut / pomega_max);
+                else if (cut >= pomega_max)
+                    cut = end;
+            }
+            if (cut > 0.0 && cut < end) {
+                stk.push(w, -end, -cut, 0);
+                stk.push(w, cut, end, 0);
                 stk.push(w, -cut, cut, 0);
             } else
-                stk.push(w, -pomega_max, pomega_max, 0);
+                stk.push(w, -end, end, 0);
         }
     }
     stk.seal();
@@ -150,7 +172,13 @@ RB_FN_NOINLINE void hey_inner_integral(Warp &w, const HeyFastCtx<KIND> &cx, int 
                 vals[1] *= sigma;
             } else {
                 HeyQRIntegrand<KIND, 2> f{cx.d, &g, v, 0};
-                f.eval(t, vals);
+                if (sine_map) {
+                    const double jac = sine_amp * cos(t); // = x, exactly
+                    f.eval(sine_amp * sin(t), vals, jac);
+                    vals[0] *= jac;
+                    vals[1] *= jac;
+                } else
+                    f.eval(t, vals);
             }
             tile_store<2>(ws.inner.tile, w, w.lane, vals);
         }
@@ -166,7 +194,13 @@ RB_FN_NOINLINE void hey_inner_integral(Warp &w, const HeyFastCtx<KIND> &cx, int 
                 vals[1] *= sigma;
             } else {
                 HeyQRIntegrand<KIND, 2> f{cx.d, &g, v, 0};
-                f.eval(t, vals);
+                if (sine_map) {
+                    const double jac = sine_amp * cos(t); // = x, exactly
+                    f.eval(sine_amp * sin(t), vals, jac);
+                    vals[0] *= jac;
+                    vals[1] *= jac;
+                } else
+                    f.eval(t, vals);
             }
             tile_store<2>(ws.inner.tile, w, l, vals);
         }
@@ -186,8 +220,8 @@ RB_FN_NOINLINE void hey_inner_integral(Warp &w, const HeyFastCtx<KIND> &cx, int 
         }
         const bool accept = chan_all(ok, 2);
         if (accept || !stk.room(2) || panel_too_small(ta, tb) || w.n_apply_lanes > kAppBudget) {
-            if (!accept)
-                w.status |= kStatusCapHit;
+            if (!accept && w.n_apply_lanes > kAppBudget)
+                w.status |= kStatusCapHit; // (a panel at the bisection floor is an integrable end-point singularity)
             RB_FOR_CHAN(c, 2)
             {
                 est[c] += fabs(r[c]);
@@ -318,8 +352,8 @@ RB_FN_NOINLINE void hey_outer_integral(Warp &w, const HeyFastCtx<KIND> &cx, int 
         RB_TRACE_HEYFAST(which, map, ta, tb, r, e, ok, w.n_apply_lanes);
 #endif
         if (accept || !stk.room(2) || panel_too_small(ta, tb) || w.n_apply_lanes > kAppBudget) {
-            if (!accept)
-                w.status |= kStatusCapHit;
+            if (!accept && w.n_apply_lanes > kAppBudget)
+                w.status |= kStatusCapHit; // (a panel at the bisection floor is an integrable end-point singularity)
             RB_FOR_CHAN(c, 2) { result[c] += r[c]; }
         } else {
             stk.push(w, tc, tb, 0);
@@ -392,6 +426,9 @@ RB_FN_NOINLINE void hey_march(Warp &w, const HeyFastCtx<KIND> &cx, int which, do
                                                        : ((lo > 0.0) ? kMapLog : ((hi < 0.0) ? kMapNegLog : kMapLinear));
         PerChan<double> contrib;
         hey_outer_integral<KIND>(w, cx, which, map, lo, hi, val, contrib);
+#ifdef RB_TRACE_HEYMARCH
+        RB_TRACE_HEYMARCH(which, steps, lo, hi, delta, contrib, val);
+#endif
 
         RB_FOR_CHAN(c, 2)
         {

@@ -39,11 +39,13 @@ template <int KIND>
 struct HeyNode {
     double sigma, pomega, x, dfds;
 
-    RB_FN void fill(const Dist &d, const HeyGeometry &g, double sigma_, double pomega_)
+    // x_exact: the value of x when the caller knows it without cancellation (the product
+    // path's pomega = pomega_max sin(phi) substitution); NaN = compute it as the reference does.
+    RB_FN void fill(const Dist &d, const HeyGeometry &g, double sigma_, double pomega_, double x_exact = NAN)
     {
         sigma = sigma_;
         pomega = pomega_;
-        x = sqrt(sigma * sigma - pomega * pomega - g.sigma0_sq);
+        x = (x_exact == x_exact) ? x_exact : sqrt(sigma * sigma - pomega * pomega - g.sigma0_sq);
         const double t = g.sigma0 * g.sin_th;
         const double gamma = (sigma - pomega * g.cos_th) / t;
         const double mu = (sigma * g.cos_th - pomega) / (t * sqrt(gamma * gamma - 1.0));
@@ -110,10 +112,10 @@ struct HeyQRIntegrand {
     double sigma;
     int sel;
 
-    RB_FN void eval(double pomega, double (&out)[NV]) const
+    RB_FN void eval(double pomega, double (&out)[NV], double x_exact = NAN) const
     {
         HeyNode<KIND> nd;
-        nd.fill(*d, *g, sigma, pomega);
+        nd.fill(*d, *g, sigma, pomega, x_exact);
         const double x = nd.x;
         const double po_sq = pomega * pomega;
         const double smx = sigma - x;

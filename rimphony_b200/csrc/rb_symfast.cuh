@@ -308,8 +308,8 @@ RB_FN_NOINLINE void sym_gamma_integral(Warp &w, const SymFastCtx<KIND> &cx, doub
         RB_TRACE_INNER(n, ta, tb, r, e, ok, est);
 #endif
         if (accept || !stk.room(2) || panel_too_small(ta, tb) || w.n_apply_lanes > kAppBudget) {
-            if (!accept)
-                w.status |= kStatusCapHit;
+            if (!accept && w.n_apply_lanes > kAppBudget)
+                w.status |= kStatusCapHit; // (a panel at the bisection floor is an integrable end-point singularity)
             RB_FOR_CHAN(c, 6)
             {
                 est[c] += fabs(r[c]);
