@@ -7,7 +7,8 @@ import ctypes
 import os
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "librimphony_b200.so")
+# RIMPHONY_B200_LIB: an alternative build of the same library (kernel tuning experiments)
+LIB_PATH = os.environ.get("RIMPHONY_B200_LIB") or os.path.join(HERE, "librimphony_b200.so")
 
 c_double_p = ctypes.POINTER(ctypes.c_double)
 c_int32_p = ctypes.POINTER(ctypes.c_int32)

@@ -97,7 +97,15 @@ RB_FN_NOINLINE void hey_inner_integral(Warp &w, const HeyFastCtx<KIND> &cx, int 
             // 434): the integrand jumps there.  Find x_g with g(x_g) = 10 (g decreases in x;
             // safeguarded Newton) and cut the pomega range at +-sqrt(sigma^2 - sigma0^2 - x_g^2).
             double cut = pomega_max;
-            {
+            // g grows towards the ends of the range (x shrinks): no cut when it stays below 10 there
+            const double x_end_sq = v * v - g.sigma0_sq - pomega_max * pomega_max;
+            bool g_reaches_cutoff = true;
+            if (x_end_sq > 0.0) {
+                const double x_end = sqrt(x_end_sq);
+                const double d_end = v - x_end;
+                g_reaches_cutoff = !(kSqrt8Over3 * d_end * sqrt(d_end) / sqrt(x_end) < kGApproximationCutoff);
+            }
+            if (g_reaches_cutoff) {
                 const double big_k = kGApproximationCutoff / kSqrt8Over3;
                 double lo = 0.0, hi = v, x = 0.5 * v;
 #pragma unroll 1

@@ -48,6 +48,7 @@ __global__ void __launch_bounds__(kThreadsPerBlock, FUSED ? 3 : 4) k_symphony(Ba
 
     for (;;) {
         long long i = next_point(a.next, w.lane);
+        const long long slot = i;
         if (a.from_reroute_list) {
             if (i >= (long long)*a.reroute_count)
                 break;
@@ -63,8 +64,20 @@ __global__ void __launch_bounds__(kThreadsPerBlock, FUSED ? 3 : 4) k_symphony(Ba
         d.norm = a.norm[i];
 
         double out6[6], lobes4[4];
-        symphony_point<KIND, FUSED, kSymGammaCap, kSymNCap>(w, d, a.s[i], a.theta[i], a.eps_gamma, a.eps_n, ws, out6,
-                                                            lobes4);
+        bool resumed = false;
+        if constexpr (!FUSED) {
+            if (a.from_reroute_list) {
+                const double *snap = a.handover + (size_t)slot * kSnapDoubles;
+                if (snap[kSnapValid] == 1.0) { // resume the chunk loop where the product path stopped
+                    symphony_tail_faithful<KIND, kSymGammaCap, kSymNCap>(w, d, a.s[i], a.theta[i], a.eps_gamma, a.eps_n,
+                                                                         ws, snap, out6, lobes4);
+                    resumed = true;
+                }
+            }
+        }
+        if (!resumed)
+            symphony_point<KIND, FUSED, kSymGammaCap, kSymNCap>(w, d, a.s[i], a.theta[i], a.eps_gamma, a.eps_n, ws,
+                                                                out6, lobes4);
 
         if (w.lane == 0) {
             bool any_nan = false;
@@ -89,9 +102,13 @@ __global__ void __launch_bounds__(kThreadsPerBlock, FUSED ? 3 : 4) k_symphony(Ba
     }
 }
 
+#ifndef RB_FAST_BLOCKS
+#define RB_FAST_BLOCKS 5 // resident CTAs per SM the product kernels are compiled for (96 registers; +5 % over 4)
+#endif
+
 // The product path: compact engine (rb_engine.cuh, rb_symfast.cuh).
 template <int KIND>
-__global__ void __launch_bounds__(kThreadsPerBlock, 4) k_symphony_fast(BatchArgs a)
+__global__ void __launch_bounds__(kThreadsPerBlock, RB_FAST_BLOCKS) k_symphony_fast(BatchArgs a)
 {
     extern __shared__ double smem[];
     const int warp = threadIdx.x >> 5;
@@ -100,9 +117,10 @@ __global__ void __launch_bounds__(kThreadsPerBlock, 4) k_symphony_fast(BatchArgs
     w.init();
 
     for (;;) {
-        const long long i = next_point(a.next, w.lane);
-        if (i >= a.n)
+        const long long ticket = next_point(a.next, w.lane);
+        if (ticket >= a.n)
             break;
+        const long long i = ordered_point(a, 0, ticket);
         w.status = 0;
         w.n_apply_lanes = 0;
 
@@ -115,15 +133,20 @@ __global__ void __launch_bounds__(kThreadsPerBlock, 4) k_symphony_fast(BatchArgs
         symphony_point_fast<KIND>(w, d, a.s[i], a.theta[i], a.eps_gamma, a.eps_n, ws, out6, lobes4);
 
         if (w.status & kStatusRerouted) {
-            // fidelity guard (rb_symfast.cuh): the faithful kernel computes this point
+            // fidelity guard (rb_symfast.cuh): the faithful kernel computes this point, resuming
+            // from the recorded chunk-loop state when there is one
+            unsigned long long slot = 0;
             if (w.lane == 0) {
-                const unsigned long long slot = atomicAdd(a.reroute_count, 1ULL);
+                slot = atomicAdd(a.reroute_count, 1ULL);
                 a.reroute_list[slot] = (int)i;
                 if (a.counters)
                     a.counters[i] = w.n_apply_lanes;
                 if (a.status)
                     atomicOr(&a.status[i], (int)kStatusRerouted);
             }
+            slot = __shfl_sync(0xffffffffu, slot, 0);
+            __syncwarp();
+            a.handover[slot * kSnapDoubles + w.lane] = ws.snap[w.lane];
             continue;
         }
 
@@ -200,7 +223,7 @@ __global__ void __launch_bounds__(kThreadsPerBlock, 4) k_heyvaerts(BatchArgs a)
 
 // The product path for rho_Q, rho_V: compact engine (rb_engine.cuh, rb_heyfast.cuh).
 template <int KIND>
-__global__ void __launch_bounds__(kThreadsPerBlock, 4) k_heyvaerts_fast(BatchArgs a)
+__global__ void __launch_bounds__(kThreadsPerBlock, RB_FAST_BLOCKS) k_heyvaerts_fast(BatchArgs a)
 {
     extern __shared__ double smem[];
     const int warp = threadIdx.x >> 5;
@@ -209,9 +232,10 @@ __global__ void __launch_bounds__(kThreadsPerBlock, 4) k_heyvaerts_fast(BatchArg
     w.init();
 
     for (;;) {
-        const long long i = next_point(a.next, w.lane);
-        if (i >= a.n)
+        const long long ticket = next_point(a.next, w.lane);
+        if (ticket >= a.n)
             break;
+        const long long i = ordered_point(a, 1, ticket);
         w.status = 0;
         w.n_apply_lanes = 0;
 

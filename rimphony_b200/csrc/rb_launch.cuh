@@ -54,8 +54,34 @@ struct BatchArgs {
     // takes its points from that list instead of from 0..n-1.
     int *reroute_list;
     unsigned long long *reroute_count;
+    double *handover; // [slot][kSnapDoubles]: chunk-loop state for the faithful continuation
     int from_reroute_list;
+    // Cost-ordered scheduling of the product kernels: k_classify sorts the points into three cost
+    // classes per kernel (expensive first); ticket t of the atomic counter maps to
+    // order[class][t - (points in the classes before)].  The per-point cost spans 10x and a
+    // warp works on one point at a time, so handing out the long points first is what keeps the
+    // tail of the persistent kernel short.
+    int *order;                       // [2 kernels][kCostClasses][n]
+    unsigned long long *class_counts; // [2 kernels][kCostClasses]
 };
+
+constexpr int kCostClasses = 3;
+
+// ticket -> point index for kernel `which` (0 = Symphony, 1 = Heyvaerts)
+__device__ __forceinline__ long long ordered_point(const BatchArgs &a, int which, long long ticket)
+{
+    const unsigned long long *cnt = a.class_counts + which * kCostClasses;
+    const int *ord = a.order + (size_t)which * kCostClasses * a.n;
+    long long t = ticket;
+#pragma unroll
+    for (int k = 0; k < kCostClasses; k++) {
+        const long long c = (long long)cnt[k];
+        if (t < c)
+            return ord[(size_t)k * a.n + t];
+        t -= c;
+    }
+    return a.n; // not reached: the classes hold n points in total
+}
 
 __device__ __forceinline__ long long next_point(unsigned long long *counter, int lane)
 {
@@ -113,6 +139,7 @@ template <int KIND>
 int stage_normalize(const BatchArgs &a, int sm_count, cudaStream_t st);
 template <int KIND>
 int stage_symphony(const BatchArgs &a, bool faithful, int sm_count, cudaStream_t st);
+int stage_classify(const BatchArgs &a, cudaStream_t st);
 template <int KIND>
 int stage_symphony_fast(const BatchArgs &a, int sm_count, cudaStream_t st);
 template <int KIND>

@@ -43,14 +43,26 @@ constexpr int kMaxChunks = 400;   // safety net of the chunk loop (the reference
 // reference's exact sequence of rule applications (MODE_FAITHFUL kernel).
 constexpr double kSensitiveN = 5e9;
 constexpr double kSensitiveFraction = 2e-4;
+// A flagged point does not start over: up to n ~ 1e9 the reference's quadrature is sound and
+// the product path reproduces it, so the faithful sequence resumes from the chunk-loop state
+// recorded at the first chunk starting beyond kHandoverN (s >= 10, where the chunk sequence
+// 1e5 x 10^k is the same for every coefficient; below that the point is re-run from scratch).
+constexpr double kHandoverN = 1e9;
+constexpr double kNegligibleExponent = 200.0; // see sym_gamma_integral
 constexpr double kTailSkipSpan = 0.25; // outer remainders of the gamma range are dropped below this span
 constexpr bool kCutAtBlendEnd = true;  // also cut the central panels where the blend meets Meissel
 
 constexpr double kNarrowPanel = 0.75; // outer panels narrower than this in u use the 7-point rule
 
+// Layout of a hand-over record (doubles): the state of the chunk loop at the first chunk that
+// starts beyond kHandoverN, for the faithful continuation (rb_symphony.cuh symphony_tail_faithful).
+constexpr int kSnapNStart = 0, kSnapDeltaN = 1, kSnapIncr = 2, kSnapValid = 3, kSnapDisc = 4, kSnapTail = 12,
+              kSnapContrib = 20, kSnapActive = 28, kSnapDoubles = 32;
+
 struct SymFastWS {
     EngLevel inner, outer;
     LeungOrder on, on1;
+    double snap[kSnapDoubles];
 };
 
 // Warp-uniform context of one point.
@@ -173,6 +185,35 @@ RB_FN_NOINLINE void sym_gamma_integral(Warp &w, const SymFastCtx<KIND> &cx, doub
     // gamma = gamma_peak + t half, t in [-1, 1]
     const double half = (gamma_plus - gamma_peak) * rel_width;
 
+    // Far below the critical harmonic J_n(z)^2 ~ exp(-2n(alpha - tanh alpha)), sech(alpha) = z/n,
+    // is beyond any power-law factor (the first harmonics of a large-s point: exponent ~ s sin(theta)).
+    // With the exponent at the peak of the gamma range above kNegligibleExponent the whole gamma
+    // integral is < e^-200 of the harmonics that make up the coefficient: it is not evaluated.
+    if (n >= kNJn) {
+        double b_, c_, s_;
+        const double x0 = sym_bessel_arg<KIND>(cx, n, gamma_peak, b_, c_, s_) / n;
+        if (x0 > 0.0 && x0 < 1.0) {
+            const double th = sqrt((1.0 - x0) * (1.0 + x0));
+            const double exponent = 2.0 * n * (log((1.0 + th) / x0) - th);
+            if (exponent > kNegligibleExponent) {
+                double *ot = ws.outer.tile;
+#ifdef RB_DEVICE_BUILD
+                if (w.lane < kEngChan)
+#else
+                for (int l = 0; l < kEngChan; l++)
+#endif
+                {
+#ifdef RB_DEVICE_BUILD
+                    const int l = w.lane;
+#endif
+                    ot[l * kEngRow + col] = 0.0;
+                    ot[(kEngChan + l) * kEngRow + col] = 0.0;
+                }
+                return;
+            }
+        }
+    }
+
     warp_fence();
 #ifdef RB_DEVICE_BUILD
     if (w.lane == 0)
@@ -239,6 +280,8 @@ RB_FN_NOINLINE void sym_gamma_integral(Warp &w, const SymFastCtx<KIND> &cx, doub
                                 t1 = t0;
                                 break;
                             }
+                            if (fabs(t1 - t0) <= 1e-5 * t1) // a panel boundary needs no more than this
+                                break;
                         }
                         if (t1 > 0.0 && t1 < span)
                             tcut = t1;
@@ -410,7 +453,55 @@ RB_FN void symphony_point_fast(Warp &w, const Dist &dist, double s, double theta
     constexpr double kDerivTol = 1e-5, kDerivStep = 1e-3;
     PanelStack stk;
 
+    bool have_snap = false;
+#ifdef RB_DEVICE_BUILD
+    if (w.lane == 0)
+#endif
+        ws.snap[kSnapValid] = 0.0;
+
     for (int chunk_no = 0; chunk_no < kMaxChunks; chunk_no++) {
+        if (!have_snap && n_lo_chunk >= kHandoverN && s >= 10.0 && s < 1e6) {
+            have_snap = true;
+            warp_fence();
+#ifdef RB_DEVICE_BUILD
+            if (w.lane == 0)
+#endif
+            {
+                ws.snap[kSnapNStart] = n_lo_chunk;
+                ws.snap[kSnapDeltaN] = delta_n;
+                ws.snap[kSnapIncr] = incr_step_factor;
+                ws.snap[kSnapValid] = 1.0;
+                ws.snap[kSnapActive] = 0.0;
+            }
+            warp_fence();
+#ifdef RB_DEVICE_BUILD
+            if ((w.lane & 3) == 0)
+#endif
+            {
+                RB_FOR_CHAN(c, kEngChan)
+                {
+                    ws.snap[kSnapDisc + c] = disc[c];
+                    ws.snap[kSnapTail + c] = tail[c];
+                    ws.snap[kSnapContrib + c] = contrib[c];
+                }
+            }
+            // active mask, assembled by lane 0 from a vote
+            unsigned mask = 0;
+#ifdef RB_DEVICE_BUILD
+            mask = __ballot_sync(0xffffffffu, active.v && (w.lane & 3) == 0);
+            unsigned packed = 0;
+            for (int c = 0; c < kEngChan; c++)
+                packed |= ((mask >> (4 * c)) & 1u) << c;
+            if (w.lane == 0)
+                ws.snap[kSnapActive] = (double)packed;
+#else
+            for (int c = 0; c < kEngChan; c++)
+                mask |= (active.v[c] ? 1u : 0u) << c;
+            ws.snap[kSnapActive] = (double)mask;
+#endif
+            warp_fence();
+        }
+
         // d G / d n at the start of the chunk
         warp_fence();
         tile_clear(w, ws.outer.tile);

@@ -167,10 +167,17 @@ struct SymGammaIntegral {
 };
 
 // The chunked adaptive integration over continuous n (symphony.rs:196-295).
+// State of the chunk loop of symphony.rs:196-295 between two chunks: what the product path
+// hands to the faithful sequence when its fidelity guard fires (rb_symfast.cuh).
+struct SymChunkState {
+    double n_start, delta_n, incr_step_factor;
+    double ans, contrib;
+};
+
 template <int KIND, bool FUSED>
 RB_FN void sym_n_integration(Warp &w, SymGammaIntegral<KIND, FUSED> &G, double n_start, unsigned want,
                              double epsrel_n, IntervalList<FUSED ? kSymNA : 1> &nlist,
-                             double (&ans)[FUSED ? kSymNA : 1])
+                             double (&ans)[FUSED ? kSymNA : 1], const SymChunkState *resume = nullptr)
 {
     constexpr int NA = FUSED ? kSymNA : 1;
     constexpr double kDerivTol = 1e-5, kTolerance = 1e5;
@@ -188,6 +195,13 @@ RB_FN void sym_n_integration(Warp &w, SymGammaIntegral<KIND, FUSED> &G, double n
     if (G.g->s < 10.0) {
         delta_n = 1.0;
         incr_step_factor = 2.0;
+    }
+    if (resume) { // single-integrand (faithful) continuation
+        n_start = resume->n_start;
+        delta_n = resume->delta_n;
+        incr_step_factor = resume->incr_step_factor;
+        ans[0] = resume->ans;
+        contrib[0] = resume->contrib;
     }
 
     ApplySeq<NA, SymGammaIntegral<KIND, FUSED>> ap{G};
@@ -320,6 +334,59 @@ RB_FN void symphony_point(Warp &w, const Dist &dist, double s, double theta, dou
     const double pre_j = two_pi_e * two_pi_e / (kSpeedLight * fabs(geom.cos_th));
     const double pre_a = -1.0 * two_pi_e * two_pi_e / (2.0 * kMassElectron * kSpeedLight * fabs(geom.cos_th));
 
+    out6[0] = total[0] * pre_j;
+    out6[1] = total[1] * pre_a;
+    out6[2] = total[2] * pre_j;
+    out6[3] = total[3] * pre_a;
+    lobes4[0] = total[4] * pre_j;
+    lobes4[1] = total[6] * pre_j;
+    lobes4[2] = total[5] * pre_a;
+    lobes4[3] = total[7] * pre_a;
+    out6[4] = lobes4[0] + lobes4[1];
+    out6[5] = lobes4[2] + lobes4[3];
+}
+
+// The faithful continuation of a point the product path handed over (rb_symfast.cuh, fidelity
+// guard): `snap` is the chunk-loop state at the first chunk beyond n ~ 1e9 (layout kSnap* of
+// rb_symfast.cuh: n_start, delta_n, incr, -, disc[8], tail[8], contrib[8], active mask).  Each
+// accumulator that was still being integrated resumes the reference's own loop
+// (symphony.rs:225-292) from there, on its own, with the reference's rule sequence.
+template <int KIND, int GAMMA_CAP, int N_CAP>
+RB_FN void symphony_tail_faithful(Warp &w, const Dist &dist, double s, double theta, double epsrel_gamma,
+                                  double epsrel_n, SymWorkspace<false, GAMMA_CAP, N_CAP> &ws, const double *snap,
+                                  double (&out6)[6], double (&lobes4)[4])
+{
+    SymGeometry geom;
+    geom.s = s;
+    geom.cos_th = cos(theta);
+    geom.sin_th = sin(theta);
+
+    IntervalList<1> glist;
+    glist.bind(ws.gamma_store, GAMMA_CAP);
+    IntervalList<1> nlist;
+    nlist.bind(ws.n_store, N_CAP);
+    SymGammaIntegral<KIND, false> G{&dist, &geom, &ws.orders, &glist, 1u, 0, epsrel_gamma};
+
+    const unsigned active = (unsigned)snap[28];
+    double total[kSymNA];
+    for (int c = 0; c < kSymNA; c++) {
+        const double disc = snap[4 + c];
+        if ((active >> c) & 1u) {
+            SymChunkState st{snap[0], snap[1], snap[2], snap[12 + c], snap[20 + c]};
+            G.sel = c;
+            G.want = 1u;
+            double ans[1];
+            sym_n_integration<KIND, false>(w, G, st.n_start, 1u, epsrel_n, nlist, ans, &st);
+            const double v = disc + ans[0];
+            total[c] = (v - v == 0.0) ? v : NAN;
+        } else {
+            total[c] = disc + snap[12 + c];
+        }
+    }
+
+    const double two_pi_e = kTwoPi * kElectronCharge;
+    const double pre_j = two_pi_e * two_pi_e / (kSpeedLight * fabs(geom.cos_th));
+    const double pre_a = -1.0 * two_pi_e * two_pi_e / (2.0 * kMassElectron * kSpeedLight * fabs(geom.cos_th));
     out6[0] = total[0] * pre_j;
     out6[1] = total[1] * pre_a;
     out6[2] = total[2] * pre_j;

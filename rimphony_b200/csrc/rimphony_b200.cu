@@ -49,6 +49,24 @@ __global__ void __launch_bounds__(256) k_dfma_peak(double *sink, int iters, doub
         sink[0] = t;
 }
 
+// Cost classes of the product kernels (rb_launch.cuh BatchArgs::order).  Symphony: rule
+// applications grow with s (500 at s < 1 to 3000 at s ~ 1e4).  Heyvaerts: s sin(theta) < 0.5
+// costs 5-13 k applications with the J/Y elements, < 3 about 3 k, the rest 1.3 k.
+__global__ void k_classify(rbhost::BatchArgs a)
+{
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= a.n)
+        return;
+    const double s = a.s[i];
+    const double sigma0 = s * sin(a.theta[i]);
+    const int cs = (s >= 300.0) ? 0 : ((s >= 10.0) ? 1 : 2);
+    const int ch = (sigma0 < 0.5) ? 0 : ((sigma0 < 3.0) ? 1 : 2); // NaN lands in the last class
+    const unsigned long long ks = atomicAdd(&a.class_counts[cs], 1ULL);
+    a.order[(size_t)cs * a.n + ks] = (int)i;
+    const unsigned long long kh = atomicAdd(&a.class_counts[rbhost::kCostClasses + ch], 1ULL);
+    a.order[(size_t)(rbhost::kCostClasses + ch) * a.n + kh] = (int)i;
+}
+
 // test entry point: the device Bessel evaluator
 __global__ void k_bessel(long long count, const double *n, const double *x, double *j, double *dj)
 {
@@ -72,6 +90,14 @@ thread_local std::string g_error;
 
 } // namespace
 namespace rbhost {
+int stage_classify(const BatchArgs &a, cudaStream_t st)
+{
+    RB_CUDA(cudaMemsetAsync(a.class_counts, 0, 2 * kCostClasses * sizeof(unsigned long long), st));
+    k_classify<<<(unsigned)((a.n + 255) / 256), 256, 0, st>>>(a);
+    g_launches++;
+    RB_CUDA(cudaGetLastError());
+    return 0;
+}
 std::atomic<uint64_t> g_launches{0};
 int fail(const char *fmt, ...)
 {
@@ -120,7 +146,7 @@ struct DeviceContext {
     cudaStream_t stream = nullptr;       // Symphony + copies
     cudaStream_t stream_hey = nullptr;   // Heyvaerts, overlaps the Symphony tail
     cudaEvent_t ev[8] = {};
-    DeviceBuffer in, out, scratch, counters, reroute;
+    DeviceBuffer in, out, scratch, counters, reroute, handover, order;
     float last_ms[4] = {0, 0, 0, 0};
     std::mutex lock;
 };
@@ -219,8 +245,10 @@ int launch_kind(DeviceContext &c, BatchArgs a, const ResolvedOptions &o, cudaStr
     RB_CUDA(cudaMemsetAsync(counters, 0, 4 * sizeof(unsigned long long), st));
     RB_CUDA(cudaEventRecord(c.ev[0], st));
 
-    // 1. normalisation
+    // 1. normalisation (+ the cost-ordered schedule of the product kernels)
     if (stage_normalize<KIND>(a, c.sm_count, st))
+        return 1;
+    if (o.mode == RIMPHONY_B200_MODE_FAST && stage_classify(a, st))
         return 1;
     RB_CUDA(cudaEventRecord(c.ev[1], st));
     if (st_hey != st)
@@ -325,10 +353,18 @@ int run_device(int kind, int64_t n, const double *s, const double *theta, const 
         return 1;
     if (c.reroute.reserve((size_t)n * sizeof(int)))
         return 1;
+    if (c.order.reserve((size_t)n * 2 * kCostClasses * sizeof(int) + 2 * kCostClasses * sizeof(unsigned long long)))
+        return 1;
+    if (o.mode == RIMPHONY_B200_MODE_FAST && (o.coeff_mask & 0x3Fu) &&
+        c.handover.reserve((size_t)n * kSnapDoubles * sizeof(double)))
+        return 1;
 
     BatchArgs a;
     memset(&a, 0, sizeof a);
     a.reroute_list = static_cast<int *>(c.reroute.ptr);
+    a.handover = static_cast<double *>(c.handover.ptr);
+    a.class_counts = static_cast<unsigned long long *>(c.order.ptr);
+    a.order = reinterpret_cast<int *>(a.class_counts + 2 * kCostClasses);
     a.n = n;
     a.s = s;
     a.theta = theta;
@@ -743,6 +779,8 @@ void rimphony_b200_shutdown(void)
         c.scratch.release();
         c.counters.release();
         c.reroute.release();
+        c.handover.release();
+        c.order.release();
         for (auto &e : c.ev)
             cudaEventDestroy(e);
         cudaStreamDestroy(c.stream);

@@ -84,13 +84,26 @@ static void run_symphony_fast(const Dist &d, double s, double theta, const doubl
     memcpy(lobes4, l4, sizeof(l4));
     info[0] = w.n_apply_lanes;
     info[1] = w.status;
-    delete ws;
-    if (w.status & kStatusRerouted) { // what the launcher does: re-run with the faithful kernel
-        unsigned info2[2];
-        run_symphony<KIND, false>(d, s, theta, eps, out6, lobes4, info2);
-        info[0] += info2[0];
-        info[1] |= info2[1] & 0xffu;
+    if (w.status & kStatusRerouted) { // what the launcher does: hand the point to the faithful kernel
+        if (ws->snap[kSnapValid] == 1.0) {
+            constexpr int GC = 1024, NC = 1024;
+            auto *fws = new SymWorkspace<false, GC, NC>();
+            Warp w2;
+            w2.init();
+            symphony_tail_faithful<KIND, GC, NC>(w2, d, s, theta, eps[0], eps[1], *fws, ws->snap, o6, l4);
+            memcpy(out6, o6, sizeof(o6));
+            memcpy(lobes4, l4, sizeof(l4));
+            info[0] += w2.n_apply_lanes;
+            info[1] |= w2.status & 0xffu;
+            delete fws;
+        } else {
+            unsigned info2[2];
+            run_symphony<KIND, false>(d, s, theta, eps, out6, lobes4, info2);
+            info[0] += info2[0];
+            info[1] |= info2[1] & 0xffu;
+        }
     }
+    delete ws;
 }
 
 template <int KIND, bool FUSED>
