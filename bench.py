@@ -129,17 +129,26 @@ def whole_job_value(points_per_rank, world, steps, ms):
     return points_per_rank * world * steps / (ms * 1e-3)
 
 
+def host_threads():
+    """Every host core this process may use.  torchrun exports OMP_NUM_THREADS=1 to its workers;
+    the CPU arm must not inherit that, it is asked for all the host threads it can use."""
+    try:
+        return max(1, len(os.sched_getaffinity(0)))
+    except AttributeError:
+        return max(1, os.cpu_count() or 1)
+
+
 def cpu_baseline(config, n_sample, kind_label):
     """The oracle (the reference's algorithm; its own bessel.c) on the host cores."""
     from oracle import oracle as O
     from rimphony_b200.sampler import synthetic_batch
 
-    threads = O.num_threads()
+    threads = host_threads()
     if n_sample <= 0:
         n_sample = max(16, 12 * threads)  # ~1 s per point per core => ~15-25 s
     kind, s, theta, params = synthetic_batch(config, n_sample, seed=SEED)
     t0 = time.perf_counter()
-    O.batch(kind, s, theta, params)
+    O.batch(kind, s, theta, params, n_threads=threads)
     dt = time.perf_counter() - t0
     return {"value": n_sample / dt, "unit": UNIT, "cores": threads, "kind": kind_label,
             "sample": f"first {n_sample} points of the seeded {config} batch, one point per OpenMP thread, "
@@ -157,14 +166,15 @@ def run_reference(args):
     from oracle import oracle as O
     from rimphony_b200.sampler import synthetic_batch
 
-    threads = O.num_threads()
+    threads = host_threads()
     n_sample = args.cpu_sample if args.cpu_sample > 0 else max(8, 4 * threads)
     kind, s, theta, params = synthetic_batch(args.config, n_sample, seed=SEED)
     for _ in range(min(args.warmup, 1)):
-        O.batch(kind, s[: max(threads, 1)], theta[: max(threads, 1)], [np.asarray(p)[: max(threads, 1)] if np.ndim(p) else p for p in params])
+        O.batch(kind, s[: max(threads, 1)], theta[: max(threads, 1)],
+                [np.asarray(p)[: max(threads, 1)] if np.ndim(p) else p for p in params], n_threads=threads)
     t0 = time.perf_counter()
     for _ in range(args.steps):
-        O.batch(kind, s, theta, params)
+        O.batch(kind, s, theta, params, n_threads=threads)
     dt = time.perf_counter() - t0
     value = args.steps * n_sample / dt
     line = {

@@ -1,0 +1,62 @@
+"""The batched crank-out tool writes the reference's on-disk format (SURVEY section 8 row f1;
+examples/crank-out-pitchypl.rs:132-155, 175-194; crank-out-pitchykappa.rs:165-216)."""
+import math
+import re
+
+import numpy as np
+import pytest
+
+from rimphony_b200 import crank_out
+
+ROW = re.compile(r"^(-?\d\.\d{16}e-?\d+|NaN|inf|-inf)(\t(-?\d\.\d{16}e-?\d+|NaN|inf|-inf))*$")
+
+
+def test_rust_scientific_format():
+    assert crank_out.rust_sci(1.0) == "1.0000000000000000e0"
+    assert crank_out.rust_sci(-0.15625) == "-1.5625000000000000e-1"
+    assert crank_out.rust_sci(1e10) == "1.0000000000000000e10"
+    assert crank_out.rust_sci(float("nan")) == "NaN"
+    assert float(crank_out.rust_sci(math.pi)) == math.pi  # 17 significant digits round-trip
+
+
+def fake_eval(tool, cols, n_devices):
+    n = len(cols["s"])
+    vals = np.outer(np.arange(1, 9), cols["s"])
+    vals[6, ::3] = np.nan
+    return vals
+
+
+@pytest.mark.parametrize("tool,argv,header", [
+    ("pitchypl", ["0.07", "1e4", "0.003", "1.5705", "1.5", "4", "0", "3"], crank_out.PITCHYPL_HEADER),
+    ("pitchykappa", ["1", "1e6", "0.003", "1.5705", "1.5", "4.5", "2.718", "20.08", "0", "3"], crank_out.PITCHYKAPPA_HEADER),
+])
+def test_tsv_layout_and_append(tmp_path, tool, argv, header):
+    path = tmp_path / "out.txt"
+    for _ in range(2):  # the second run appends and re-emits the header, like the reference
+        crank_out.main(["--block", "7", "--count", "17", "--seed", "3", tool] + argv + [str(path)], evaluate_fn=fake_eval)
+    lines = path.read_text().splitlines()
+    assert len(lines) == 2 * (1 + 17)
+    assert lines[0] == "\t".join(header) and lines[18] == lines[0]
+    n_par = len(header) - 9
+    for ln in lines[1:18]:
+        assert ROW.match(ln), ln
+        f = ln.split("\t")
+        assert len(f) == len(header)
+        s = float(f[0])
+        lo, hi = float(argv[0]), float(argv[1])
+        assert lo <= s <= hi
+        assert float(f[n_par + 1 + 2]) == pytest.approx(3 * s, rel=1e-15)  # j_Q column of the fake evaluator
+    assert sum("NaN" in ln for ln in lines[1:18]) >= 5
+
+
+@pytest.mark.gpu
+def test_crank_out_on_the_device(tmp_path):
+    path = tmp_path / "pl.txt"
+    crank_out.main(["--block", "64", "--count", "64", "--seed", "1", "pitchypl", "1", "100", "0.3", "1.5", "2", "3", "0", "2",
+                    str(path)])
+    rows = np.array([[float(x) for x in ln.split("\t")] for ln in path.read_text().splitlines()[1:]])
+    assert rows.shape == (64, 13)
+    assert (rows[:, 5] > 0).all() and np.isfinite(rows[:, 5:11]).all()
+    import rimphony_b200 as R
+    again = R.compute_all_dimensionless_batch(R.PITCHY_PL, rows[:, 0], rows[:, 1], [rows[:, 2], rows[:, 3], 1.0, 1e12, 1e10])
+    assert np.array_equal(again.values.T, rows[:, 5:], equal_nan=True)
