@@ -77,7 +77,7 @@ RB_FN double lgamma_stirling(double n, double ln_n, double ninv)
     return (n - 0.5) * ln_n - n + 0.918938533204672741780329736405618 + series;
 }
 
-RB_FN void leung_prepare(double n, LeungOrder &o)
+RB_FN_NOINLINE void leung_prepare(double n, LeungOrder &o)
 {
     o.n = n;
     if (!(n >= 0.0)) {
@@ -93,11 +93,11 @@ RB_FN void leung_prepare(double n, LeungOrder &o)
     o.kind = kOrderLeung;
     o.nint = 0;
     const double ninv = 1.0 / n;
-    const double ln_n = log(n);
+    const double ln_n = rb_log(n);
     o.ninv = ninv;
 
     // eta thresholds -0.6666666 log10 n + intercept, as bounds on eps itself
-    const double pw = exp(kEtaSlope * ln_n); // n^-0.6666666
+    const double pw = rb_exp(kEtaSlope * ln_n); // n^-0.6666666
     o.lo_minus = pw * kTenMinusA;
     o.hi_minus = pw * kTenMinusB;
     o.lo_plus = pw * kTenPlusA;
@@ -125,14 +125,16 @@ RB_FN double exp_factor(double f_factor, double f_exp)
         return f_factor *
                (1.0 + ((40320.0 + (20160.0 + (6720.0 + (1680.0 + (336.0 + (56.0 + (8.0 + x) * x) * x) * x) * x) * x) * x) * x / 40320.0));
     }
+    // (one exp call site for the three cases of bessel.c:40-50)
+    double mult = f_factor, arg = f_exp;
     if (fabs_exp > 690.0) {
-        const double sign_f = (f_factor < 0.0) ? -1.0 : 1.0;
-        const double log_f = log(fabs(f_factor));
-        if (log_f * f_exp < 0.0)
-            return sign_f * exp(log_f + f_exp);
-        return f_factor * exp(f_exp);
+        const double log_f = rb_log(fabs(f_factor));
+        if (log_f * f_exp < 0.0) {
+            mult = (f_factor < 0.0) ? -1.0 : 1.0;
+            arg = log_f + f_exp;
+        }
     }
-    return f_factor * exp(f_exp);
+    return mult * rb_exp(arg);
 }
 
 // Meissel's first expansion, x < n (bessel.c:94-149).
@@ -176,7 +178,7 @@ RB_FN double leung_meissel_first(const LeungOrder &o, double x)
             inv_zp1 = 1.0 + (-1.0 + (1.0 + (-1.0 + (1.0 + (-1.0 + (1.0 - Z) * Z) * Z) * Z) * Z) * Z) * Z;
         else
             inv_zp1 = 1.0 / (1.0 + Z);
-        exp_val = n * (log(x * inv_zp1) - (1.0 - Z)) - vsum1 + o.c_std;
+        exp_val = n * (rb_log(x * inv_zp1) - (1.0 - Z)) - vsum1 + o.c_std;
     }
     return exp_factor(factor, exp_val);
 }
@@ -219,7 +221,7 @@ RB_FN double leung_debye_eps(double n, double x)
         return NAN;
 
     const double ez = x - n;
-    const double z = cbrt(x);
+    const double z = rb_cbrt(x);
     const double t3 = z * z;
     const double t4 = x * z;
     const double t10 = t4 * t4;
@@ -321,7 +323,7 @@ RB_FN double leung_j(const LeungOrder &o, double x)
             return leung_meissel_first(o, x);
         const double debye = leung_debye_eps(n, x);
         const double meissel1 = leung_meissel_first(o, x);
-        const double eta = log(eps) * kLog10e;
+        const double eta = rb_log(eps) * kLog10e;
         const double pos = (eta - o.eta_lo_minus) / (kMinusEtaB - kMinusEtaA);
         return debye * (1.0 - pos) + meissel1 * pos;
     } else {
@@ -332,7 +334,7 @@ RB_FN double leung_j(const LeungOrder &o, double x)
             return leung_meissel_second(n, x);
         const double debye = leung_debye_eps(n, x);
         const double meissel2 = leung_meissel_second(n, x);
-        const double eta = log(eps) * kLog10e;
+        const double eta = rb_log(eps) * kLog10e;
         const double pos = (eta - o.eta_lo_plus) / (kPlusEtaB - kPlusEtaA);
         return debye * (1.0 - pos) + meissel2 * pos;
     }

@@ -7,8 +7,8 @@
 //   src/pitchy_pl.rs:32-64, 95-115         PitchyPowerLawDistribution
 //   src/pitchy_kappa.rs:38-62, 90-125      PitchyKappaDistribution
 //
-// f, df/dgamma and df/dcos(xi) are produced together: they share one exp() and
-// one or two log() per call (gamma^-p exp(-gamma/gc) sin^k(xi) is evaluated as a
+// f, df/dgamma and df/dcos(xi) are produced together: they share one rb_exp() and
+// one or two rb_log() per call (gamma^-p rb_exp(-gamma/gc) sin^k(xi) is evaluated as a
 // single exponential), instead of the reference's separate powf/exp per term.
 #pragma once
 
@@ -76,7 +76,7 @@ RB_HD bool dist_from_params(const double *pv, int n_params, Dist &d)
 // sin^k(xi) given sin^2(xi); pow(x, 0) = 1 for every x including NaN.
 RB_FN double log_pitch_term(double k, double sin2)
 {
-    return (k == 0.0) ? 0.0 : 0.5 * k * log(sin2);
+    return (k == 0.0) ? 0.0 : 0.5 * k * rb_log(sin2);
 }
 
 // calc_f and calc_f_derivatives in one go.
@@ -89,12 +89,12 @@ RB_FN void dist_eval(const Dist &d, double gamma, double cos_xi, double &f, doub
             return;
         }
         const double g2m1 = gamma * gamma - 1.0;
-        // norm gamma^-p exp(-gamma/gc) / (gamma^2 beta),  gamma^2 beta = gamma sqrt(gamma^2 - 1)
-        f = d.norm * exp(-d.p * log(gamma) - gamma * d.inv_gamma_cutoff) / (gamma * sqrt(g2m1));
+        // norm gamma^-p rb_exp(-gamma/gc) / (gamma^2 beta),  gamma^2 beta = gamma sqrt(gamma^2 - 1)
+        f = d.norm * rb_exp(-d.p * rb_log(gamma) - gamma * d.inv_gamma_cutoff) / (gamma * sqrt(g2m1));
         dfdg = -f * ((d.p + 1.0) / gamma + gamma / g2m1 + d.inv_gamma_cutoff);
         dfdcx = 0.0;
     } else if (KIND == kDistThermalJuettner) {
-        f = d.norm * exp(d.neg_inverse_t * gamma);
+        f = d.norm * rb_exp(d.neg_inverse_t * gamma);
         dfdg = f * d.neg_inverse_t;
         dfdcx = 0.0;
     } else if (KIND == kDistPitchyPL) {
@@ -104,14 +104,14 @@ RB_FN void dist_eval(const Dist &d, double gamma, double cos_xi, double &f, doub
         }
         const double sin2 = 1.0 - cos_xi * cos_xi;
         const double g2m1 = gamma * gamma - 1.0;
-        f = d.norm * exp(log_pitch_term(d.k, sin2) - d.p * log(gamma) - gamma * d.inv_gamma_cutoff) /
+        f = d.norm * rb_exp(log_pitch_term(d.k, sin2) - d.p * rb_log(gamma) - gamma * d.inv_gamma_cutoff) /
             (gamma * sqrt(g2m1));
         dfdg = -f * ((d.p + 1.0) / gamma + gamma / g2m1 + d.inv_gamma_cutoff);
         dfdcx = -f * d.k * cos_xi / sin2;
     } else {
         const double sin2 = 1.0 - cos_xi * cos_xi;
-        f = d.norm * exp(log_pitch_term(d.k, sin2) -
-                         (d.kappa + 1.0) * log(1.0 + (gamma - 1.0) * d.inv_kappa_width) -
+        f = d.norm * rb_exp(log_pitch_term(d.k, sin2) -
+                         (d.kappa + 1.0) * rb_log(1.0 + (gamma - 1.0) * d.inv_kappa_width) -
                          gamma * d.inv_gamma_cutoff);
         dfdg = -f * ((d.kappa + 1.0) / (d.kappa * d.width + gamma - 1.0) + d.inv_gamma_cutoff);
         dfdcx = -f * d.k * cos_xi / sin2;
@@ -122,7 +122,7 @@ RB_FN void dist_eval(const Dist &d, double gamma, double cos_xi, double &f, doub
 
 struct PLNormIntegrand {
     double p, inv_gamma_cutoff;
-    RB_FN void eval(double g, double (&out)[1]) const { out[0] = exp(-p * log(g) - g * inv_gamma_cutoff); }
+    RB_FN void eval(double g, double (&out)[1]) const { out[0] = rb_exp(-p * rb_log(g) - g * inv_gamma_cutoff); }
 };
 
 struct KappaNormIntegrand {
@@ -130,7 +130,7 @@ struct KappaNormIntegrand {
     RB_FN void eval(double g, double (&out)[1]) const
     {
         out[0] = g * sqrt(g * g - 1.0) *
-                 exp(-(kappa + 1.0) * log(1.0 + (g - 1.0) * inv_kappa_width) - g * inv_gamma_cutoff);
+                 rb_exp(-(kappa + 1.0) * rb_log(1.0 + (g - 1.0) * inv_kappa_width) - g * inv_gamma_cutoff);
     }
 };
 
@@ -138,11 +138,11 @@ struct KappaNormIntegrand {
 // (what gsl_sf_hyperg_2F1 returns at x = 1; pitchy_pl.rs:98, pitchy_kappa.rs:93).
 RB_FN double pitch_angle_integral(double k)
 {
-    return 0.886226925452758013649083741670573 * exp(lgamma(1.0 + 0.5 * k) - lgamma(1.5 + 0.5 * k));
+    return 0.886226925452758013649083741670573 * rb_exp(lgamma(1.0 + 0.5 * k) - lgamma(1.5 + 0.5 * k));
 }
 
-// int_1^inf g sqrt(g^2-1) exp(-g/T) dg = T K_2(1/T), with K_2 from the
-// trapezoid rule on int_0^inf exp(-z cosh t) cosh 2t dt (lanes split the
+// int_1^inf g sqrt(g^2-1) rb_exp(-g/T) dg = T K_2(1/T), with K_2 from the
+// trapezoid rule on int_0^inf rb_exp(-z cosh t) cosh 2t dt (lanes split the
 // abscissae).  The reference uses QAGIU with epsrel 1e-5
 // (thermal_juettner.rs:56-64); the closed form is what that converges to.
 RB_FN double juettner_gamma_integral(const Warp &w, double t)
@@ -156,7 +156,7 @@ RB_FN double juettner_gamma_integral(const Warp &w, double t)
         const double arg = z * cosh(tt);
         const bool live = arg <= 745.0;
         if (live)
-            sum += ((i == 0) ? 0.5 : 1.0) * exp(-arg) * cosh(2.0 * tt);
+            sum += ((i == 0) ? 0.5 : 1.0) * rb_exp(-arg) * cosh(2.0 * tt);
         if (__all_sync(0xffffffffu, !live))
             break;
     }
@@ -168,7 +168,7 @@ RB_FN double juettner_gamma_integral(const Warp &w, double t)
         const double arg = z * cosh(tt);
         if (arg > 745.0)
             break;
-        sum += ((i == 0) ? 0.5 : 1.0) * exp(-arg) * cosh(2.0 * tt);
+        sum += ((i == 0) ? 0.5 : 1.0) * rb_exp(-arg) * cosh(2.0 * tt);
     }
 #endif
     return t * sum * h;

@@ -44,7 +44,7 @@ struct HeyFastCtx {
 };
 
 enum { kHeyNR = 0, kHeyQR = 1 };
-// how the outer variable is mapped: v = t, v = exp(t), v = -exp(t), v = v_lo + t^2
+// how the outer variable is mapped: v = t, v = rb_exp(t), v = -rb_exp(t), v = v_lo + t^2
 enum { kMapLinear = 0, kMapLog = 1, kMapNegLog = 2, kMapSqrt = 3 };
 
 // Note on NaN: at the isolated points of the (sigma, pomega) plane where gamma = 1 a power law's
@@ -78,7 +78,7 @@ RB_FN_NOINLINE void hey_inner_integral(Warp &w, const HeyFastCtx<KIND> &cx, int 
         if (!(sigma_max > sigma_min)) {
             empty = true;
         } else {
-            const double t_lo = log(sigma_min), t_hi = log(sigma_max);
+            const double t_lo = rb_log(sigma_min), t_hi = rb_log(sigma_max);
             int n_seed = (int)ceil((t_hi - t_lo) / kHeyPanelWidth);
             n_seed = n_seed < 1 ? 1 : (n_seed > 8 ? 8 : n_seed);
             for (int k = n_seed - 1; k >= 0; k--) // the lowest panel (largest values) is popped first
@@ -86,7 +86,7 @@ RB_FN_NOINLINE void hey_inner_integral(Warp &w, const HeyFastCtx<KIND> &cx, int 
         }
     } else {
         // heyvaerts.rs:262-296: pomega in [-pomega_max, pomega_max]
-        const double pomega_max_phys = sqrt(kThreeTwoThirds * cbrt(v) * v - g.sigma0_sq);
+        const double pomega_max_phys = sqrt(kThreeTwoThirds * rb_cbrt(v) * v - g.sigma0_sq);
         const double pomega_max_qr = sqrt(v * v - g.sigma0_sq);
         const double pomega_max = fmin(pomega_max_phys, pomega_max_qr);
         if (!(pomega_max > 0.0) && pomega_max == pomega_max)
@@ -173,7 +173,7 @@ RB_FN_NOINLINE void hey_inner_integral(Warp &w, const HeyFastCtx<KIND> &cx, int 
             double vals[2];
             const double t = tc + thl * w.xk;
             if (which == kHeyNR) {
-                const double sigma = exp(t);
+                const double sigma = rb_exp(t);
                 HeyNRIntegrand<KIND, 2> f{cx.d, &g, v, 0};
                 f.eval(sigma, vals);
                 vals[0] *= sigma;
@@ -195,7 +195,7 @@ RB_FN_NOINLINE void hey_inner_integral(Warp &w, const HeyFastCtx<KIND> &cx, int 
             double vals[2];
             const double t = tc + thl * LANE_X[l];
             if (which == kHeyNR) {
-                const double sigma = exp(t);
+                const double sigma = rb_exp(t);
                 HeyNRIntegrand<KIND, 2> f{cx.d, &g, v, 0};
                 f.eval(sigma, vals);
                 vals[0] *= sigma;
@@ -275,9 +275,9 @@ RB_FN_NOINLINE void hey_outer_integral(Warp &w, const HeyFastCtx<KIND> &cx, int 
         t_lo = 0.0;
         t_hi = sqrt(v_hi - v_lo);
     } else {
-        // v = +-exp(t); for the negative branch t runs from ln|v_hi| to ln|v_lo|
-        t_lo = (map == kMapLog) ? log(v_lo) : log(-v_hi);
-        t_hi = (map == kMapLog) ? log(v_hi) : log(-v_lo);
+        // v = +-rb_exp(t); for the negative branch t runs from ln|v_hi| to ln|v_lo|
+        t_lo = (map == kMapLog) ? rb_log(v_lo) : rb_log(-v_hi);
+        t_hi = (map == kMapLog) ? rb_log(v_hi) : rb_log(-v_lo);
     }
     const double offset = v_lo;
     {
@@ -288,7 +288,7 @@ RB_FN_NOINLINE void hey_outer_integral(Warp &w, const HeyFastCtx<KIND> &cx, int 
         if (which == kHeyNR) {
             const double p_star = cx.g.sigma0 * cx.g.cos_th / cx.g.sin_th;
             if (p_star > v_lo && p_star < v_hi)
-                t_star = (map == kMapLinear) ? p_star : log(p_star); // p_star > 0: linear or log map
+                t_star = (map == kMapLinear) ? p_star : rb_log(p_star); // p_star > 0: linear or log map
         }
         const double max_w = (map == kMapLog || map == kMapNegLog) ? kHeyPanelWidth : INFINITY;
         // upper segment [t_star, t_hi] first so that the lower one is popped first
@@ -339,7 +339,7 @@ RB_FN_NOINLINE void hey_outer_integral(Warp &w, const HeyFastCtx<KIND> &cx, int 
                 v = offset + t * t;
                 jac = 2.0 * t;
             } else if (map != kMapLinear) {
-                jac = exp(t);
+                jac = rb_exp(t);
                 v = (map == kMapLog) ? jac : -jac;
             }
             hey_inner_integral<KIND>(w, cx, which, v, tile_col(j), rwk[j] * jac, rwd[j] * jac);

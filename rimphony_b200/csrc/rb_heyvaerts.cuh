@@ -41,7 +41,7 @@ struct HeyNode {
 
     // x_exact: the value of x when the caller knows it without cancellation (the product
     // path's pomega = pomega_max sin(phi) substitution); NaN = compute it as the reference does.
-    RB_FN void fill(const Dist &d, const HeyGeometry &g, double sigma_, double pomega_, double x_exact = NAN)
+    RB_MFN_NOINLINE void fill(const Dist &d, const HeyGeometry &g, double sigma_, double pomega_, double x_exact = NAN)
     {
         sigma = sigma_;
         pomega = pomega_;

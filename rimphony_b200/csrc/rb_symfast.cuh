@@ -12,7 +12,7 @@
 //   * the gamma integral is seeded where the integrand lives.  For large n the
 //     integrand is a peak of relative half-width ~ n^(-1/3) around gamma_peak:
 //     with gamma = gamma_peak + t (gamma_+ - gamma_peak), z/n = 1 - t^2/2 - ... and
-//     J_n(z)^2 ~ exp(-(2n/3) |t|^3).  The seeds are [-T, 0], [0, T] with
+//     J_n(z)^2 ~ rb_exp(-(2n/3) |t|^3).  The seeds are [-T, 0], [0, T] with
 //     T = kPeakSpan n^(-1/3) plus the two outer remainders, instead of the
 //     reference's bisection cascade from the full [gamma_-, gamma_+] (15-45 rule
 //     applications per gamma integral at n >= 1e3, measured);
@@ -91,7 +91,7 @@ RB_FN double leung_j_below(const LeungOrder &o, double x)
     if (use_meissel)
         mv = leung_meissel_first(o, x);
     if (use_debye && use_meissel) {
-        const double eta = log(eps) * kLog10e;
+        const double eta = rb_log(eps) * kLog10e;
         const double pos = (eta - o.eta_lo_minus) / (kMinusEtaB - kMinusEtaA);
         return dv * (1.0 - pos) + mv * pos;
     }
@@ -120,6 +120,15 @@ RB_FN double sym_bessel_arg(const SymFastCtx<KIND> &cx, double n, double gamma, 
         gamma_sin_xi = sqrt(r * (gamma * (gamma + s_on_r)) - (n * n / (s * s * beta2_costh2)));
     }
     return s * beta * sinth * gamma_sin_xi;
+}
+
+// eps = (n - z)/n at gamma, for the seed placement: one out-of-line copy (it is called from
+// five places of the warp-uniform seeding code).
+template <int KIND>
+RB_FN_NOINLINE double sym_eps_at(const SymFastCtx<KIND> &cx, double n, double gamma)
+{
+    double b_, c_, s_;
+    return (n - sym_bessel_arg<KIND>(cx, n, gamma, b_, c_, s_)) / n;
 }
 
 // The six gamma integrands at one node (symphony.rs:398-479).
@@ -181,20 +190,19 @@ RB_FN_NOINLINE void sym_gamma_integral(Warp &w, const SymFastCtx<KIND> &cx, doub
     const double gamma_minus = (nos - fabs(costh) * root) / sin2;
     const double gamma_plus = (nos + fabs(costh) * root) / sin2;
     const double gamma_peak = 0.5 * (gamma_plus + gamma_minus);
-    const double rel_width = (s < 1e6) ? 1.0 : exp(-0.27 * log(n) - 0.1);
+    const double rel_width = (s < 1e6) ? 1.0 : rb_exp(-0.27 * rb_log(n) - 0.1);
     // gamma = gamma_peak + t half, t in [-1, 1]
     const double half = (gamma_plus - gamma_peak) * rel_width;
 
-    // Far below the critical harmonic J_n(z)^2 ~ exp(-2n(alpha - tanh alpha)), sech(alpha) = z/n,
+    // Far below the critical harmonic J_n(z)^2 ~ rb_exp(-2n(alpha - tanh alpha)), sech(alpha) = z/n,
     // is beyond any power-law factor (the first harmonics of a large-s point: exponent ~ s sin(theta)).
     // With the exponent at the peak of the gamma range above kNegligibleExponent the whole gamma
     // integral is < e^-200 of the harmonics that make up the coefficient: it is not evaluated.
     if (n >= kNJn) {
-        double b_, c_, s_;
-        const double x0 = sym_bessel_arg<KIND>(cx, n, gamma_peak, b_, c_, s_) / n;
+        const double x0 = 1.0 - sym_eps_at<KIND>(cx, n, gamma_peak);
         if (x0 > 0.0 && x0 < 1.0) {
             const double th = sqrt((1.0 - x0) * (1.0 + x0));
-            const double exponent = 2.0 * n * (log((1.0 + th) / x0) - th);
+            const double exponent = 2.0 * n * (rb_log((1.0 + th) / x0) - th);
             if (exponent > kNegligibleExponent) {
                 double *ot = ws.outer.tile;
 #ifdef RB_DEVICE_BUILD
@@ -231,13 +239,13 @@ RB_FN_NOINLINE void sym_gamma_integral(Warp &w, const SymFastCtx<KIND> &cx, doub
     // seed is then smooth and is usually accepted at its first application.
     PanelStack stk;
     stk.reset(&ws.inner);
-    const double w_peak = exp(-(1.0 / 3.0) * log(n));
+    const double w_peak = rb_exp(-(1.0 / 3.0) * rb_log(n));
     double span = kPeakSpan * w_peak / rel_width;
     const bool full = !(span < 0.5);
     if (full)
         span = 1.0;
     else if (!(span < kTailSkipSpan)) {
-        // Beyond |t| = T the Bessel factor is below exp(-(2/3) kPeakSpan^3) of its peak while f
+        // Beyond |t| = T the Bessel factor is below rb_exp(-(2/3) kPeakSpan^3) of its peak while f
         // grows at most like (1 - |t|)^-(p+2); the remainders are integrated only while T is
         // not yet small (n <~ 2000), as a guard for the mildly relativistic regime.
         stk.push(w, -1.0, -span, 0);
@@ -248,8 +256,7 @@ RB_FN_NOINLINE void sym_gamma_integral(Warp &w, const SymFastCtx<KIND> &cx, doub
         const bool leung = n >= kNJn;
         warp_fence(); // orders prepared by lane 0
         const double lo = ws.on.lo_minus, hi = ws.on.hi_minus;
-        double b_, c_, s_;
-        const double eps0 = leung ? (n - sym_bessel_arg<KIND>(cx, n, gamma_peak, b_, c_, s_)) / n : 0.0;
+        const double eps0 = leung ? sym_eps_at<KIND>(cx, n, gamma_peak) : 0.0;
 #pragma unroll 1
         for (int side = 0; side < 2; side++) {
             const double sgn = side ? 1.0 : -1.0;
@@ -262,13 +269,12 @@ RB_FN_NOINLINE void sym_gamma_integral(Warp &w, const SymFastCtx<KIND> &cx, doub
                     double t0 = sqrt(2.0 * (target - eps0)) / rel_width;
                     if (t0 < span) {
                         double t1 = 1.05 * t0;
-                        double f0 = (n - sym_bessel_arg<KIND>(cx, n, gamma_peak + half * sgn * t0, b_, c_, s_)) / n - target;
+                        double f0 = sym_eps_at<KIND>(cx, n, gamma_peak + half * sgn * t0) - target;
 #pragma unroll 1
                         for (int it = 0; it < 4; it++) {
                             if (!(t1 < 1.0))
                                 t1 = 0.5 * (t0 + 1.0);
-                            const double f1 =
-                                (n - sym_bessel_arg<KIND>(cx, n, gamma_peak + half * sgn * t1, b_, c_, s_)) / n - target;
+                            const double f1 = sym_eps_at<KIND>(cx, n, gamma_peak + half * sgn * t1) - target;
                             const double den = f1 - f0;
                             if (den == 0.0 || !(den == den))
                                 break;
@@ -525,7 +531,7 @@ RB_FN void symphony_point_fast(Warp &w, const Dist &dist, double s, double theta
             delta_n *= incr_step_factor;
 
         // the chunk, cut into panels of at most kPanelWidth in u; the rightmost is popped first
-        const double u_lo = log(n_lo_chunk), u_hi = log(n_lo_chunk + delta_n);
+        const double u_lo = rb_log(n_lo_chunk), u_hi = rb_log(n_lo_chunk + delta_n);
         int n_seed = (int)ceil((u_hi - u_lo) / kPanelWidth);
         if (n_seed < 1)
             n_seed = 1;
@@ -561,7 +567,7 @@ RB_FN void symphony_point_fast(Warp &w, const Dist &dist, double s, double theta
             filled = n_nodes;
 #pragma unroll 1
             for (int j = 0; j < n_nodes; j++) {
-                const double n = exp(uc + uhl * rx[j]);
+                const double n = rb_exp(uc + uhl * rx[j]);
                 sym_gamma_integral<KIND>(w, cx, n, tile_col(j), rwk[j] * n, rwd[j] * n);
             }
             warp_fence();

@@ -139,6 +139,9 @@ struct SymGammaIntegral {
 #ifdef RB_TRACE_G
         const unsigned apps_before = w.n_apply_lanes;
 #endif
+#ifdef RB_TRACE_GF
+        const unsigned apps_before_f = w.n_apply_lanes;
+#endif
         SymGammaIntegrand<KIND, NV> f{d, g, ord, n, 0};
         ApplyLanes<NV, SymGammaIntegrand<KIND, NV>> ap{f};
 
@@ -162,6 +165,9 @@ struct SymGammaIntegral {
                 bounds[1] = gamma_peak;
             }
             qag_joint<PolicyPlain<1>>(w, ap, 1, bounds, epsrel, *list, 1u, out);
+#ifdef RB_TRACE_GF
+            RB_TRACE_GF(n, sel, w.n_apply_lanes - apps_before_f, out[0]);
+#endif
         }
     }
 };

@@ -40,7 +40,8 @@ def compare(got, want, lobes, mask):
 def main():
     mask = int(sys.argv[1], 0) if len(sys.argv) > 1 else 0xFF
     n_tp = int(sys.argv[2]) if len(sys.argv) > 2 else 32768
-    for name in ("pitchy_pl", "symphony_rows", "powerlaw", "pitchy_kappa", "juettner_sweep", "pitchy_pl_4k"):
+    only_tp = os.environ.get("FAST_CHECK_ONLY_THROUGHPUT") == "1"
+    for name in (() if only_tp else ("pitchy_pl", "symphony_rows", "powerlaw", "pitchy_kappa", "juettner_sweep", "pitchy_pl_4k")):
         path = os.path.join(ROOT, "tests", "golden", name + ".npz")
         if not os.path.exists(path):
             continue
@@ -57,7 +58,7 @@ def main():
               f"GK apps mean sym {res.counters[0].mean():.0f} hey {res.counters[1].mean():.0f}")
         compare(res.values, fx["out"], fx["lobes"], m)
 
-    for cfg in ("pitchy_pl", "pitchy_kappa"):
+    for cfg in (("pitchy_pl",) if only_tp else ("pitchy_pl", "pitchy_kappa")):
         n_cfg = n_tp if cfg == "pitchy_pl" else max(1024, n_tp // 8)  # kappa: ~23 % of points take the faithful route
         kind, s, th, params = R.synthetic_batch(cfg, n_cfg, seed=1)
         for mk, tag in ((0x3F, "symphony only"), (0xC0, "heyvaerts only"), (0xFF, "all 8")):
