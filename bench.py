@@ -37,11 +37,12 @@ SEED = 20260
 
 # FP64 floating-point operations executed per 31-node Gauss-Kronrod application (FMA = 2): ncu
 # smsp__sass_thread_inst_executed_op_{dfma,dmul,dadd}_pred_on over one launch of each product
-# kernel divided by the applications that launch counted (profiles/r01_fast_kernels_details.txt,
-# 4096 seeded pitchy power-law points: 2127 / 1037 flop per SM-clock cycle over 48.0 / 231.8 ms).
-FLOP_PER_APPLICATION = {"symphony": 45.7e3, "heyvaerts": 25.3e3}
-# DRAM bytes (read + write) per point of the same captures: the path does not touch HBM.
-DRAM_BYTES_PER_POINT = {"symphony": (324.9e3 + 5.07e6) / 4096, "heyvaerts": (671.5e3 + 2.91e6) / 4096}
+# kernel divided by the applications that launch counted (profiles/r01_fast_kernels_details.txt and
+# r01_fast_kernels_summary.md: 4096 seeded pitchy power-law points, 38.5 / 145.7 ms).
+FLOP_PER_APPLICATION = {"symphony": 46.6e3, "heyvaerts": 26.15e3}
+# DRAM bytes (read + write) per point of the same captures (register spills to local memory; the
+# algorithmic traffic is ~110 B per point): the path does not touch HBM.
+DRAM_BYTES_PER_POINT = {"symphony": (0.764e6 + 13.78e6) / 4096, "heyvaerts": (1.366e6 + 32.16e6) / 4096}
 
 
 def parse():

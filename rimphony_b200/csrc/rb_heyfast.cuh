@@ -30,6 +30,7 @@ namespace rb {
 constexpr double kHeyInnerFloor = 1.0;
 constexpr double kHeyPanelWidth = 2.0; // widest panel in the log of the variable
 constexpr double kHeyDerivStep = 1e-4; // relative step of the derivative probe
+constexpr int kHeyOuterMaxDepth = 13;  // bisections below a seed after which an outer panel is declared divergent
 
 struct HeyFastWS {
     EngLevel inner, outer;
@@ -355,17 +356,38 @@ RB_FN_NOINLINE void hey_outer_integral(Warp &w, const HeyFastCtx<KIND> &cx, int 
             big[c] = fmax(big[c], fabs(r[c]));
             ok[c] = panel_ok(r[c], e[c], cx.epsrel_outer, fmax(fabs(scale[c]) + fabs(result[c]), big[c]));
         }
-        const bool accept = chan_all(ok, 2);
+        bool accept = chan_all(ok, 2);
 #ifdef RB_TRACE_HEYFAST
         RB_TRACE_HEYFAST(which, map, ta, tb, r, e, ok, w.n_apply_lanes);
 #endif
+        // An outer panel that still fails kHeyOuterMaxDepth bisections below its seed sits on a
+        // non-integrable point of the outer integrand (for s sin(theta) < 3 the QR domain contains
+        // sigma = s, pomega = s cos(theta), where gamma = 1 and a power law's df/dsigma diverges
+        // like (gamma - 1)^-3/2 while the QR elements stay finite): the integral does not exist.
+        // The reference's QAG reports an error there (-> NaN); so does this path, without spending
+        // the application budget on it.
+        if (!accept && tag >= kHeyOuterMaxDepth) {
+            RB_FOR_CHAN(c, 2)
+            {
+                if (!ok[c])
+                    result[c] = NAN;
+            }
+            w.status |= kStatusCapHit;
+            accept = true;
+        }
         if (accept || !stk.room(2) || panel_too_small(ta, tb) || w.n_apply_lanes > kAppBudget) {
             if (!accept && w.n_apply_lanes > kAppBudget)
                 w.status |= kStatusCapHit; // (a panel at the bisection floor is an integrable end-point singularity)
             RB_FOR_CHAN(c, 2) { result[c] += r[c]; }
+            // nothing left to integrate for once both coefficients are NaN
+            PerChan<bool> dead;
+            RB_FOR_CHAN(c, kEngChan) { dead[c] = true; }
+            RB_FOR_CHAN(c, 2) { dead[c] = !(result[c] == result[c]); }
+            if (chan_all(dead, 2))
+                return;
         } else {
-            stk.push(w, tc, tb, 0);
-            stk.push(w, ta, tc, 0);
+            stk.push(w, tc, tb, tag + 1);
+            stk.push(w, ta, tc, tag + 1);
             stk.seal();
         }
     }
