@@ -323,6 +323,52 @@ class FullSynchrotronCalculator(SynchrotronCalculator):
         return self._batch(np.atleast_1d(np.asarray(s, dtype=np.float64)), theta, 0xFF, extras=extras)
 
 
+class _PowerLawHighFrequency(SynchrotronCalculator):
+    """``HighFrequencyApproximation`` of src/power_law.rs:119-170: closed-form Faraday coefficients
+    (Huang & Shcherbakov 2011), a checker for the full calculation.  Host arithmetic, as in the
+    reference; everything but (Faraday, Q) and (Faraday, V) is NaN."""
+
+    def __init__(self, distrib):
+        self.distrib = distrib
+
+    def compute_dimensionless(self, coeff, stokes, s, theta):
+        d = self.distrib
+        s, theta = np.asarray(s, dtype=np.float64), np.asarray(theta, dtype=np.float64)
+        p, gmin = np.asarray(d.p, dtype=np.float64), np.asarray(d.gamma_min, dtype=np.float64)
+        if Coefficient(coeff) != Coefficient.Faraday or Stokes(stokes) == Stokes.I:
+            out = np.full(np.broadcast(s, theta, p).shape, np.nan)
+        elif Stokes(stokes) == Stokes.Q:  # power_law.rs:146-152
+            out = (0.0085 * 2.0 / (p - 2.0) * ((s / (np.sin(theta) * gmin ** 2)) ** ((p - 2.0) / 2.0) - 1.0) *
+                   (p - 1.0) / gmin ** (1.0 - p) * (np.sin(theta) / s) ** ((p + 2.0) / 2.0))
+        else:  # power_law.rs:155-161
+            out = 0.017 * (np.log(gmin) * (p - 1.0)) / ((p + 1.0) * gmin ** 2) / s * np.sin(theta)
+        return float(out) if np.ndim(out) == 0 else out
+
+
+class _ThermalHighFrequency(SynchrotronCalculator):
+    """``HighFrequencyApproximation`` of src/thermal_juettner.rs:92-142 (Heyvaerts' high-frequency
+    limits with K_0, K_1, K_2 of 1/T)."""
+
+    def __init__(self, distrib):
+        self.distrib = distrib
+
+    def compute_dimensionless(self, coeff, stokes, s, theta):
+        from scipy.special import kve  # exponentially scaled: the ratios below are scale-free
+
+        s, theta = np.asarray(s, dtype=np.float64), np.asarray(theta, dtype=np.float64)
+        t = np.asarray(self.distrib.t, dtype=np.float64)
+        inv_t = 1.0 / t
+        factor = 2.0 * ELECTRON_CHARGE * ELECTRON_CHARGE / MASS_ELECTRON
+        k0, k1, k2 = kve(0, inv_t), kve(1, inv_t), kve(2, inv_t)
+        if Coefficient(coeff) != Coefficient.Faraday or Stokes(stokes) == Stokes.I:
+            out = np.full(np.broadcast(s, theta, t).shape, np.nan)
+        elif Stokes(stokes) == Stokes.Q:  # thermal_juettner.rs:112-127
+            out = factor * np.sin(theta) ** 2 * (k1 + 6.0 * t * k2) / (2.0 * SPEED_LIGHT * s ** 2 * k2)
+        else:  # thermal_juettner.rs:129-141
+            out = factor * np.cos(theta) * k0 / (SPEED_LIGHT * s * k2)
+        return float(out) if np.ndim(out) == 0 else out
+
+
 class _Distribution:
     KIND = -1
 
@@ -378,6 +424,10 @@ class PowerLawDistribution(_Distribution):
     def _columns(self):
         return [self.p, self.gamma_min, self.gamma_max, self._gamma_cutoff]
 
+    def high_freq_approximation(self):
+        """src/power_law.rs:112-115"""
+        return _PowerLawHighFrequency(self)
+
 
 class ThermalJuettnerDistribution(_Distribution):
     """src/thermal_juettner.rs:23-50: f ~ exp(-gamma/T)."""
@@ -388,6 +438,10 @@ class ThermalJuettnerDistribution(_Distribution):
 
     def _columns(self):
         return [self.t]
+
+    def high_freq_approximation(self):
+        """src/thermal_juettner.rs:74-77"""
+        return _ThermalHighFrequency(self)
 
 
 class PitchyPowerLawDistribution(_Distribution):

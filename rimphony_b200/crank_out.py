@@ -4,6 +4,7 @@
     python -m rimphony_b200.crank_out pitchypl   S_MIN S_MAX THETA_MIN THETA_MAX P_MIN P_MAX K_MIN K_MAX OUTFILE
     python -m rimphony_b200.crank_out pitchykappa S_MIN S_MAX THETA_MIN THETA_MAX KAPPA_MIN KAPPA_MAX \\
                                                   WIDTH_MIN WIDTH_MAX K_MIN K_MAX OUTFILE
+    python -m rimphony_b200.crank_out demo almostuniform1          # examples/demo-powerlaw.rs, to stdout
 
 Same positional arguments (crank-out-pitchypl.rs:17-74, crank-out-pitchykappa.rs:17-92), same
 sampling (``Sampler``: s and width log-uniform, the rest uniform), same output file: opened
@@ -28,7 +29,39 @@ PITCHYPL_HEADER = ("s(log)", "theta(lin)", "p(lin)", "k(lin)", "time_ms(meta)", 
 PITCHYKAPPA_HEADER = ("s(log)", "theta(lin)", "kappa(lin)", "width(log)", "k(lin)", "time_ms(meta)", "j_I(res)",
                       "alpha_I(res)", "j_Q(res)", "alpha_Q(res)", "j_V(res)", "alpha_V(res)", "rho_Q(res)", "rho_V(res)")
 
+DEMO_HEADER = ("s(lin)", "theta(lin)", "p(lin)", "d(meta)", "psi(meta)", "n_e(meta)", "time_ms(meta)", "j_I(res)",
+               "alpha_I(res)", "j_Q(res)", "alpha_Q(res)", "j_V(res)", "alpha_V(res)", "rho_Q(res)", "rho_V(res)")
+
 GAMMA_MIN, GAMMA_MAX, GAMMA_CUTOFF = 1.0, 1e12, 1e10  # crank-out-pitchypl.rs:163-165
+
+
+def demo_almostuniform1():
+    """The 64-step sweep of examples/demo-powerlaw.rs:80-98 (neurosynchro's end-to-end fixture)."""
+    x = np.arange(64) / 63.0
+    return {"s": 100.0 - 10.0 * x, "theta": 0.5 + 0.1 * x, "p": 3.0 - 0.5 * x, "d": x * 3e10, "psi": 0.1 * x,
+            "n_e": 1e5 - 3e4 * x}
+
+
+def evaluate_demo(cols, n_devices=1):
+    import rimphony_b200 as R
+
+    res = R.compute_all_dimensionless_batch(R.POWER_LAW, cols["s"], cols["theta"],
+                                            [cols["p"], GAMMA_MIN, GAMMA_MAX, GAMMA_CUTOFF])
+    return res.values
+
+
+def run_demo(name, out, evaluate_fn=evaluate_demo):
+    if name != "almostuniform1":
+        raise SystemExit(f"unknown demo {name!r} (the reference has: almostuniform1)")
+    cols = demo_almostuniform1()
+    n = len(cols["s"])
+    t0 = time.perf_counter()
+    vals = evaluate_fn(cols)
+    ms = (time.perf_counter() - t0) * 1e3 / n
+    out.write("\t".join(DEMO_HEADER) + "\n")
+    out.write(format_rows([cols["s"], cols["theta"], cols["p"], cols["d"], cols["psi"], cols["n_e"], np.full(n, ms)] +
+                          [vals[c] for c in range(8)]))
+    return 0
 
 
 def rust_sci(x):
@@ -63,6 +96,8 @@ def parse(argv):
                  "K_MIN", "K_MAX"):
         pk.add_argument(name, type=float)
     pk.add_argument("OUTFILE")
+    dm = sub.add_parser("demo")
+    dm.add_argument("DEMONAME", choices=["almostuniform1"])
     return ap.parse_args(argv)
 
 
@@ -95,6 +130,8 @@ def evaluate(tool, cols, n_devices):
 
 def main(argv=None, evaluate_fn=evaluate):
     args = parse(sys.argv[1:] if argv is None else argv)
+    if args.tool == "demo":
+        return run_demo(args.DEMONAME, sys.stdout)
     rng = np.random.default_rng(args.seed)
     header, samp = samplers(args, rng)
     done = 0

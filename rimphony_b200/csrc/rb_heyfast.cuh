@@ -228,6 +228,9 @@ RB_FN_NOINLINE void hey_inner_integral(Warp &w, const HeyFastCtx<KIND> &cx, int 
             ok[c] = panel_ok(r[c], e[c], cx.epsrel_inner, kHeyInnerFloor * fmax(est[c] + fabs(r[c]), big[c]));
         }
         const bool accept = chan_all(ok, 2);
+#ifdef RB_TRACE_HEYINNER
+        RB_TRACE_HEYINNER(which, v, ta, tb, r, e, ok, sine_map);
+#endif
         if (accept || !stk.room(2) || panel_too_small(ta, tb) || w.n_apply_lanes > kAppBudget) {
             if (!accept && w.n_apply_lanes > kAppBudget)
                 w.status |= kStatusCapHit; // (a panel at the bisection floor is an integrable end-point singularity)

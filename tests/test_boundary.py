@@ -184,3 +184,20 @@ def test_bench_reference_arm_line(tmp_path):
     assert line["impl"] == "reference" and line["unit"] == "coefficient-sets/s" and line["value"] > 0
     assert line["cpu_baseline"]["kind"] == "port" and line["e2e"]["h2d_bytes_per_step"] == 0
     assert line["higher_is_better"] is True and line["dtype"] == "f64"
+
+
+def test_high_frequency_approximations_known_answers():
+    """power_law.rs:200-207, 224-231; thermal_juettner.rs:174-181, 194-201 (1 %)."""
+    C, S = R.Coefficient, R.Stokes
+    pl = R.PowerLawDistribution(2.5).gamma_limits(10.0, 1e12, 1e10).high_freq_approximation()
+    assert pl.compute_dimensionless(C.Faraday, S.Q, 1e4, 0.25 * math.pi) == pytest.approx(1.81e-9, rel=0.01)
+    assert pl.compute_dimensionless(C.Faraday, S.V, 1e4, 0.25 * math.pi) == pytest.approx(1.19e-8, rel=0.01)
+    assert (R.ThermalJuettnerDistribution(10.0).high_freq_approximation()
+            .compute_dimensionless(C.Faraday, S.Q, 4e4, 0.4)) == pytest.approx(4.8081e-11, rel=0.01)
+    assert (R.ThermalJuettnerDistribution(0.1).high_freq_approximation()
+            .compute_dimensionless(C.Faraday, S.V, 40.0, 0.5)) == pytest.approx(3.064e-4, rel=0.01)
+    assert math.isnan(pl.compute_dimensionless(C.Emission, S.I, 1e4, 0.5))
+    assert math.isnan(pl.compute_dimensionless(C.Faraday, S.I, 1e4, 0.5))
+    # array arguments evaluate a batch
+    q = pl.compute_dimensionless(C.Faraday, S.Q, np.array([1e3, 1e4]), 0.25 * math.pi)
+    assert q.shape == (2,) and q[1] == pytest.approx(1.81e-9, rel=0.01)

@@ -49,6 +49,28 @@ def test_tsv_layout_and_append(tmp_path, tool, argv, header):
     assert sum("NaN" in ln for ln in lines[1:18]) >= 5
 
 
+def test_demo_powerlaw_layout():
+    """examples/demo-powerlaw.rs:63-99, 123-163."""
+    import io
+    buf = io.StringIO()
+    crank_out.run_demo("almostuniform1", buf, evaluate_fn=lambda cols: np.outer(np.arange(1, 9), cols["s"]))
+    lines = buf.getvalue().splitlines()
+    assert lines[0] == "\t".join(crank_out.DEMO_HEADER) and len(lines) == 65
+    first, last = [float(v) for v in lines[1].split("\t")], [float(v) for v in lines[-1].split("\t")]
+    assert first[:6] == [100.0, 0.5, 3.0, 0.0, 0.0, 1e5]
+    assert last[:6] == pytest.approx([90.0, 0.6, 2.5, 3e10, 0.1, 7e4], rel=1e-15)
+    assert all(ROW.match(ln) for ln in lines[1:])
+
+
+@pytest.mark.gpu
+def test_demo_powerlaw_on_the_device():
+    import io
+    buf = io.StringIO()
+    crank_out.run_demo("almostuniform1", buf)
+    rows = np.array([[float(x) for x in ln.split("\t")] for ln in buf.getvalue().splitlines()[1:]])
+    assert rows.shape == (64, 15) and np.isfinite(rows[:, 7:]).all() and (rows[:, 7] > 0).all()
+
+
 @pytest.mark.gpu
 def test_crank_out_on_the_device(tmp_path):
     path = tmp_path / "pl.txt"

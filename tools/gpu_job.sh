@@ -1,4 +1,6 @@
 set -x
-python tools/profile_small.py 4096 0xFF > gpurun_out/plain_fast4.log 2>&1 && ncu --set full --clock-control none --import-source on -k regex:'k_symphony_fast|k_heyvaerts_fast' -c 2 -o gpurun_out/prof_fast4 -f python tools/profile_small.py 4096 0xFF > gpurun_out/ncu_fast4.log 2>&1
-python bench.py --points 32768 --steps 2 --warmup 3 --no-cpu-baseline > gpurun_out/bench6.log 2>&1 && ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/launches_r01c.csv python bench.py --points 32768 --steps 2 --warmup 3 --no-cpu-baseline > gpurun_out/ncu_bench3.log 2>&1
-cat gpurun_out/plain_fast4.log; tail -3 gpurun_out/ncu_fast4.log
+python -m pytest tests -m gpu -q > gpurun_out/pytest_gpu7.log 2>&1; echo "pytest exit $?" >> gpurun_out/pytest_gpu7.log
+python bench.py > gpurun_out/bench7.log 2>&1
+FAST_CHECK_ONLY_THROUGHPUT=1 python tools/fast_check.py 0xFF 131072 > gpurun_out/fast7.log 2>&1
+python tools/fast_check.py 0xC0 1024 > gpurun_out/fast7_hey.log 2>&1
+tail -5 gpurun_out/pytest_gpu7.log | cut -c1-250; cut -c1-2600 gpurun_out/bench7.log; grep throughput gpurun_out/fast7.log | cut -c1-200; grep -A2 "pitchy_pl_4k\|juettner" gpurun_out/fast7_hey.log | cut -c1-260
