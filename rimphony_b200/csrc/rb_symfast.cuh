@@ -28,7 +28,7 @@
 
 namespace rb {
 
-constexpr double kPeakSpan = 3.2;    // seed half-width in units of n^(-1/3)
+constexpr double kPeakSpan = 2.6;    // seed half-width in units of n^(-1/3): exp(-(2/3) 2.6^3) = 8e-6, tail beyond < 1e-6
 constexpr double kInnerFloor = 1.0; // acceptance floor of a gamma panel, fraction of the integral so far
 constexpr double kPanelWidth = 2.302585092994046; // outer panel width in u = ln n (one decade)
 constexpr int kMaxChunks = 400;   // safety net of the chunk loop (the reference has none)
@@ -131,9 +131,15 @@ RB_FN_NOINLINE double sym_eps_at(const SymFastCtx<KIND> &cx, double n, double ga
     return (n - sym_bessel_arg<KIND>(cx, n, gamma, b_, c_, s_)) / n;
 }
 
-// The six gamma integrands at one node (symphony.rs:398-479).
+// The six gamma integrands at one node (symphony.rs:398-479).  Out of line: it is the body of
+// both the shared-application pass and the 31-point loop, and the kernel is fetch-bound.
 template <int KIND>
-RB_FN void sym_node(const SymFastCtx<KIND> &cx, double n, double gamma, double (&out)[6])
+#ifdef RB_SYM_SHARED_APPLICATIONS
+RB_FN_NOINLINE void sym_node( // two call sites: keep one copy
+#else
+RB_FN void sym_node(
+#endif
+const SymFastCtx<KIND> &cx, double n, double gamma, double (&out)[6])
 {
     const double costh = cx.cos_th, sinth = cx.sin_th;
     double beta, cos_xi, sin_xi;
@@ -244,15 +250,12 @@ RB_FN_NOINLINE void sym_gamma_integral(Warp &w, const SymFastCtx<KIND> &cx, doub
     const bool full = !(span < 0.5);
     if (full)
         span = 1.0;
-    else if (!(span < kTailSkipSpan)) {
-        // Beyond |t| = T the Bessel factor is below rb_exp(-(2/3) kPeakSpan^3) of its peak while f
-        // grows at most like (1 - |t|)^-(p+2); the remainders are integrated only while T is
-        // not yet small (n <~ 2000), as a guard for the mildly relativistic regime.
-        stk.push(w, -1.0, -span, 0);
-        stk.push(w, span, 1.0, 1);
-    }
+    // Beyond |t| = T the Bessel factor is below exp(-(2/3) kPeakSpan^3) of its peak while f grows
+    // at most like (1 - |t|)^-(p+2); the remainders [+-T, +-1] are integrated only while T is not
+    // yet small (n <~ 1000), as a guard for the mildly relativistic regime.
+    const bool keep_remainders = !full && !(span < kTailSkipSpan);
+    double cut[2][2]; // [side][which]: 0 < |cut0| <= |cut1| <= span, or == span when absent
     {
-        double cut[2][2]; // [side][which]: 0 < |cut0| <= |cut1| <= span, or == span when absent
         const bool leung = n >= kNJn;
         warp_fence(); // orders prepared by lane 0
         const double lo = ws.on.lo_minus, hi = ws.on.hi_minus;
@@ -297,16 +300,8 @@ RB_FN_NOINLINE void sym_gamma_integral(Warp &w, const SymFastCtx<KIND> &cx, doub
             }
             if (cut[side][0] > cut[side][1])
                 cut[side][0] = cut[side][1];
-            // panels [0, c0], [c0, c1], [c1, span]; empty ones are skipped
-            const double c0 = cut[side][0], c1 = cut[side][1];
-            if (span > c1)
-                stk.push(w, side ? c1 : -span, side ? span : -c1, side);
-            if (c1 > c0)
-                stk.push(w, side ? c0 : -c1, side ? c1 : -c0, side);
-            stk.push(w, side ? 0.0 : -c0, side ? c0 : 0.0, side);
         }
     }
-    stk.seal();
 
     // est: integral of |f| over the accepted panels; big: the largest |panel value| seen so far,
     // accepted or not (the central seeds are evaluated first, so it knows the scale at once)
@@ -318,6 +313,122 @@ RB_FN_NOINLINE void sym_gamma_integral(Warp &w, const SymFastCtx<KIND> &cx, doub
         est[c] = 0.0;
         big[c] = 0.0;
     }
+
+    // The usual case at n >~ 2000: three smooth panels per side and no remainders.  They are
+    // small enough for lower-order rules, so they share applications: the two central panels
+    // as two 15-point Kronrod rules (lanes 0-14, 16-30), then the four blend / tail panels
+    // (~1 % of the integral) as four 7-point rules (one per quarter of the warp).  A panel that
+    // misses its tolerance goes to the stack and gets the regular 31-point treatment below.
+    // EXPERIMENT, off by default (-DRB_SYM_SHARED_APPLICATIONS): rule applications per point drop
+    // from 1023 to 646, but on the B200 the kernel gets SLOWER (1221 ms vs 1003 ms at 131 072
+    // points): a shared application runs every Bessel branch (Debye, blend, Meissel) in one warp
+    // instead of one branch per panel, and the extra per-panel bookkeeping is warp-uniform code.
+#ifdef RB_SYM_SHARED_APPLICATIONS
+    const bool six_panels = cut[0][0] > 0.0 && cut[0][0] < cut[0][1] && cut[0][1] < span && cut[1][0] > 0.0 &&
+                            cut[1][0] < cut[1][1] && cut[1][1] < span;
+#else
+    const bool six_panels = false;
+#endif
+    // a third shared application (two 15-point rules) takes the outer remainders while they are kept
+    const int n_pass = keep_remainders ? 3 : 2;
+    if (six_panels) {
+#pragma unroll 1
+        for (int pass = 0; pass < n_pass; pass++) {
+            const int npart = (pass == 1) ? 4 : 2;
+            // panel p of this pass: [pa[p], pb[p]], side ps[p]
+            double pa[4], pb[4];
+            int ps[4];
+            if (pass == 0) {
+                pa[0] = -cut[0][0], pb[0] = 0.0, ps[0] = 0;
+                pa[1] = 0.0, pb[1] = cut[1][0], ps[1] = 1;
+                pa[2] = pa[3] = pb[2] = pb[3] = 0.0, ps[2] = ps[3] = 0;
+            } else if (pass == 2) {
+                pa[0] = -1.0, pb[0] = -span, ps[0] = 0;
+                pa[1] = span, pb[1] = 1.0, ps[1] = 1;
+                pa[2] = pa[3] = pb[2] = pb[3] = 0.0, ps[2] = ps[3] = 0;
+            } else {
+                pa[0] = -span, pb[0] = -cut[0][1], ps[0] = 0;
+                pa[1] = -cut[0][1], pb[1] = -cut[0][0], ps[1] = 0;
+                pa[2] = cut[1][0], pb[2] = cut[1][1], ps[2] = 1;
+                pa[3] = cut[1][1], pb[3] = span, ps[3] = 1;
+            }
+            double hl[4];
+#pragma unroll
+            for (int p = 0; p < 4; p++)
+                hl[p] = 0.5 * (pb[p] - pa[p]) * half;
+            warp_fence(); // previous reads of the tile are done
+#ifdef RB_DEVICE_BUILD
+            {
+                const int l = w.lane;
+                const bool k7 = (pass == 1);
+                const int p = k7 ? (l >> 3) : (l >> 4);
+                const double x = k7 ? L7_X[l] : L15_X[l];
+                const double wk = k7 ? L7_WK[l] : L15_WK[l];
+                const double wd = k7 ? L7_WD[l] : L15_WD[l];
+                double vals[6];
+                sym_node<KIND>(cx, n, gamma_peak + half * (0.5 * (pa[p] + pb[p]) + 0.5 * (pb[p] - pa[p]) * x), vals);
+                tile_store_weighted<6>(ws.inner.tile, l, wk, wd, vals);
+            }
+#else
+            for (int l = 0; l < 32; l++) {
+                const bool k7 = (pass == 1);
+                const int p = k7 ? (l >> 3) : (l >> 4);
+                const double x = k7 ? L7_X[l] : L15_X[l];
+                const double wk = k7 ? L7_WK[l] : L15_WK[l];
+                const double wd = k7 ? L7_WD[l] : L15_WD[l];
+                double vals[6];
+                sym_node<KIND>(cx, n, gamma_peak + half * (0.5 * (pa[p] + pb[p]) + 0.5 * (pb[p] - pa[p]) * x), vals);
+                tile_store_weighted<6>(ws.inner.tile, l, wk, wd, vals);
+            }
+#endif
+            w.n_apply_lanes++;
+            warp_fence();
+
+            PerChan<double> pr[4], pe[4];
+            tile_reduce_parts(ws.inner.tile, 6, npart, hl, pr, pe);
+#pragma unroll 1
+            for (int p = 0; p < npart; p++) {
+                PerChan<bool> ok;
+                RB_FOR_CHAN(c, kEngChan) { ok[c] = true; }
+                RB_FOR_CHAN(c, 6)
+                {
+                    big[c] = fmax(big[c], fabs(pr[p][c]));
+                    ok[c] = panel_ok(pr[p][c], pe[p][c], cx.epsrel_gamma, kInnerFloor * fmax(est[c] + fabs(pr[p][c]), big[c]));
+                }
+                if (chan_all(ok, 6)) {
+                    RB_FOR_CHAN(c, 6)
+                    {
+                        est[c] += fabs(pr[p][c]);
+                        if (ps[p])
+                            sum_r[c] += pr[p][c];
+                        else
+                            sum_l[c] += pr[p][c];
+                    }
+                } else {
+#ifdef RB_TRACE_MULTI
+                    RB_TRACE_MULTI(n, pass, p, pr[p], pe[p], est, big);
+#endif
+                    stk.push(w, pa[p], pb[p], ps[p]);
+                }
+            }
+        }
+    } else {
+        if (keep_remainders) {
+            stk.push(w, -1.0, -span, 0);
+            stk.push(w, span, 1.0, 1);
+        }
+#pragma unroll 1
+        for (int side = 0; side < 2; side++) {
+            // panels [0, c0], [c0, c1], [c1, span]; empty ones are skipped
+            const double c0 = cut[side][0], c1 = cut[side][1];
+            if (span > c1)
+                stk.push(w, side ? c1 : -span, side ? span : -c1, side);
+            if (c1 > c0)
+                stk.push(w, side ? c0 : -c1, side ? c1 : -c0, side);
+            stk.push(w, side ? 0.0 : -c0, side ? c0 : 0.0, side);
+        }
+    }
+    stk.seal();
 
     while (stk.sp > 0) {
         double ta, tb;
@@ -380,6 +491,9 @@ RB_FN_NOINLINE void sym_gamma_integral(Warp &w, const SymFastCtx<KIND> &cx, doub
         }
     }
 
+#ifdef RB_TRACE_GEND
+    RB_TRACE_GEND(n, w.n_apply_lanes);
+#endif
     // park the eight accumulators in the outer tile
     double *ot = ws.outer.tile;
 #ifdef RB_DEVICE_BUILD

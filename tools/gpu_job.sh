@@ -1,6 +1,7 @@
-set -x
-python -m pytest tests -m gpu -q > gpurun_out/pytest_gpu7.log 2>&1; echo "pytest exit $?" >> gpurun_out/pytest_gpu7.log
-python bench.py > gpurun_out/bench7.log 2>&1
-FAST_CHECK_ONLY_THROUGHPUT=1 python tools/fast_check.py 0xFF 131072 > gpurun_out/fast7.log 2>&1
-python tools/fast_check.py 0xC0 1024 > gpurun_out/fast7_hey.log 2>&1
-tail -5 gpurun_out/pytest_gpu7.log | cut -c1-250; cut -c1-2600 gpurun_out/bench7.log; grep throughput gpurun_out/fast7.log | cut -c1-200; grep -A2 "pitchy_pl_4k\|juettner" gpurun_out/fast7_hey.log | cut -c1-260
+export FAST_CHECK_ONLY_THROUGHPUT=1
+for v in A B C D; do
+  if [ $v = A ]; then unset RIMPHONY_B200_LIB; else export RIMPHONY_B200_LIB=$PWD/rimphony_b200/csrc/_exp$v/lib_$v.so; fi
+  python tools/fast_check.py 0x3F 131072 > gpurun_out/abcd_$v.log 2>&1
+  python tools/fast_check.py 0x3F 131072 > gpurun_out/abcd_${v}2.log 2>&1
+  echo "variant $v: $(grep 'symphony only' gpurun_out/abcd_${v}2.log | cut -c1-170)"
+done
