@@ -72,6 +72,7 @@ RB_FN_NOINLINE void hey_inner_integral(Warp &w, const HeyFastCtx<KIND> &cx, int 
     // makes x = pomega_max cos(phi) and the integrand analytic in phi.
     bool sine_map = false;
     double sine_amp = 0.0;
+    double nr_sigma_min = 0.0;
     if (which == kHeyNR) {
         // heyvaerts.rs:213-250: sigma in [sigma_min, sigma_min^1.5 / sqrt(3)], in t = ln sigma
         const double sigma_min = sqrt(v * v + g.sigma0_sq);
@@ -79,7 +80,12 @@ RB_FN_NOINLINE void hey_inner_integral(Warp &w, const HeyFastCtx<KIND> &cx, int 
         if (!(sigma_max > sigma_min)) {
             empty = true;
         } else {
-            const double t_lo = rb_log(sigma_min), t_hi = rb_log(sigma_max);
+            // sigma = sigma_min cosh(t): x = sigma_min sinh(t) exactly, d sigma = x dt.  Near the
+            // lower end (x -> 0, where the integrand has algebraic end-point behaviour, strongest
+            // around the cusp pomega*) t is linear in x; far out it is ln sigma.
+            nr_sigma_min = sigma_min;
+            const double ratio = sigma_max / sigma_min;
+            const double t_lo = 0.0, t_hi = rb_log(ratio + sqrt((ratio - 1.0) * (ratio + 1.0)));
             int n_seed = (int)ceil((t_hi - t_lo) / kHeyPanelWidth);
             n_seed = n_seed < 1 ? 1 : (n_seed > 8 ? 8 : n_seed);
             for (int k = n_seed - 1; k >= 0; k--) // the lowest panel (largest values) is popped first
@@ -174,11 +180,13 @@ RB_FN_NOINLINE void hey_inner_integral(Warp &w, const HeyFastCtx<KIND> &cx, int 
             double vals[2];
             const double t = tc + thl * w.xk;
             if (which == kHeyNR) {
-                const double sigma = rb_exp(t);
+                const double et = rb_exp(t), eti = 1.0 / et;
+                const double sigma = nr_sigma_min * 0.5 * (et + eti);
+                const double x = nr_sigma_min * 0.5 * (et - eti);
                 HeyNRIntegrand<KIND, 2> f{cx.d, &g, v, 0};
-                f.eval(sigma, vals);
-                vals[0] *= sigma;
-                vals[1] *= sigma;
+                f.eval(sigma, vals, x);
+                vals[0] *= x;
+                vals[1] *= x;
             } else {
                 HeyQRIntegrand<KIND, 2> f{cx.d, &g, v, 0};
                 if (sine_map) {
@@ -196,11 +204,13 @@ RB_FN_NOINLINE void hey_inner_integral(Warp &w, const HeyFastCtx<KIND> &cx, int 
             double vals[2];
             const double t = tc + thl * LANE_X[l];
             if (which == kHeyNR) {
-                const double sigma = rb_exp(t);
+                const double et = rb_exp(t), eti = 1.0 / et;
+                const double sigma = nr_sigma_min * 0.5 * (et + eti);
+                const double x = nr_sigma_min * 0.5 * (et - eti);
                 HeyNRIntegrand<KIND, 2> f{cx.d, &g, v, 0};
-                f.eval(sigma, vals);
-                vals[0] *= sigma;
-                vals[1] *= sigma;
+                f.eval(sigma, vals, x);
+                vals[0] *= x;
+                vals[1] *= x;
             } else {
                 HeyQRIntegrand<KIND, 2> f{cx.d, &g, v, 0};
                 if (sine_map) {

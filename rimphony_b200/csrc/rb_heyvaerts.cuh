@@ -73,10 +73,10 @@ struct HeyNRIntegrand {
     double pomega;
     int sel; // 0 = h (rho_Q), 1 = f (rho_V) when NV == 1
 
-    RB_FN void eval(double sigma, double (&out)[NV]) const
+    RB_FN void eval(double sigma, double (&out)[NV], double x_exact = NAN) const
     {
         HeyNode<KIND> nd;
-        nd.fill(*d, *g, sigma, pomega);
+        nd.fill(*d, *g, sigma, pomega, x_exact);
         const double s_sq = sigma * sigma;
         const double x_sq = nd.x * nd.x;
         const double v = s_sq - x_sq;
