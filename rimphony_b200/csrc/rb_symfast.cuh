@@ -260,6 +260,62 @@ RB_FN_NOINLINE void sym_gamma_integral(Warp &w, const SymFastCtx<KIND> &cx, doub
         warp_fence(); // orders prepared by lane 0
         const double lo = ws.on.lo_minus, hi = ws.on.hi_minus;
         const double eps0 = leung ? sym_eps_at<KIND>(cx, n, gamma_peak) : 0.0;
+
+        // The four cuts at once: lane group g = 2 side + which samples eps(t) at eight points around
+        // the quadratic guess t0 = sqrt(2 (target - eps0)) (one evaluation per lane instead of
+        // ~20 warp-uniform ones), a ballot finds the bracketing pair and a linear interpolation
+        // between them places the cut to ~1e-3 of its panel.  A cut that is not bracketed falls
+        // back to the secant iteration below.
+        double found[2][2];
+        {
+#ifdef RB_DEVICE_BUILD
+            const int grp = w.lane >> 3, j = w.lane & 7;
+            const double tgt = (grp & 1) ? hi : lo;
+            const double sg = (grp & 2) ? 1.0 : -1.0;
+            const double t0g = sqrt(2.0 * (tgt - eps0)) / rel_width; // NaN when there is no crossing
+            const double tj = t0g * (0.7 + (0.6 / 7.0) * j);
+            const bool valid = leung && (eps0 < tgt) && (1.3 * t0g < span);
+            double fj = 0.0;
+            if (valid)
+                fj = sym_eps_at<KIND>(cx, n, gamma_peak + half * sg * tj) - tgt;
+            const unsigned below = __ballot_sync(0xffffffffu, valid && fj < 0.0);
+            const unsigned bits = (below >> (8 * grp)) & 0xffu;
+            const int cnt = __popc(bits);
+            const bool ok = valid && cnt >= 1 && cnt <= 7 && bits == ((1u << cnt) - 1u);
+            const int src = 8 * grp + (ok ? cnt - 1 : 0);
+            const double fa = __shfl_sync(0xffffffffu, fj, src), ta = __shfl_sync(0xffffffffu, tj, src);
+            const double fb = __shfl_sync(0xffffffffu, fj, src + 1), tb = __shfl_sync(0xffffffffu, tj, src + 1);
+            const double tcross = ok ? ta - fa * (tb - ta) / (fb - fa) : NAN;
+#pragma unroll
+            for (int g = 0; g < 4; g++)
+                found[g >> 1][g & 1] = __shfl_sync(0xffffffffu, tcross, 8 * g);
+#else
+            for (int g = 0; g < 4; g++) {
+                const double tgt = (g & 1) ? hi : lo;
+                const double sg = (g & 2) ? 1.0 : -1.0;
+                const double t0g = sqrt(2.0 * (tgt - eps0)) / rel_width;
+                const bool valid = leung && (eps0 < tgt) && (1.3 * t0g < span);
+                double tcross = NAN;
+                if (valid) {
+                    double fj[8], tj[8];
+                    int cnt = 0;
+                    bool mono = true;
+                    for (int j = 0; j < 8; j++) {
+                        tj[j] = t0g * (0.7 + (0.6 / 7.0) * j);
+                        fj[j] = sym_eps_at<KIND>(cx, n, gamma_peak + half * sg * tj[j]) - tgt;
+                        if (fj[j] < 0.0) {
+                            if (cnt != j)
+                                mono = false;
+                            cnt++;
+                        }
+                    }
+                    if (mono && cnt >= 1 && cnt <= 7)
+                        tcross = tj[cnt - 1] - fj[cnt - 1] * (tj[cnt] - tj[cnt - 1]) / (fj[cnt] - fj[cnt - 1]);
+                }
+                found[g >> 1][g & 1] = tcross;
+            }
+#endif
+        }
 #pragma unroll 1
         for (int side = 0; side < 2; side++) {
             const double sgn = side ? 1.0 : -1.0;
@@ -267,6 +323,9 @@ RB_FN_NOINLINE void sym_gamma_integral(Warp &w, const SymFastCtx<KIND> &cx, doub
             for (int k = 0; k < 2; k++) {
                 const double target = k ? hi : lo;
                 double tcut = span;
+                if (found[side][k] > 0.0 && found[side][k] < span && (k == 0 || kCutAtBlendEnd)) {
+                    tcut = found[side][k];
+                } else
                 if (leung && eps0 < target && (k == 0 || kCutAtBlendEnd)) {
                     // eps(t) ~ eps0 + (t rel_width)^2 / 2; refine on the exact function
                     double t0 = sqrt(2.0 * (target - eps0)) / rel_width;
