@@ -114,6 +114,52 @@ RB_FN_NOINLINE void leung_prepare(double n, LeungOrder &o)
     o.c_stirling = 0.5 * (ln_n - 1.837877066409345483560659472811235) + loggamma_exp - vsum2;
 }
 
+// Polynomial coefficients of the expansions below live in the constant bank and are used as
+// c[bank][offset] operands of DFMA/DMUL.  As literals the compiler materialises each 64-bit value
+// with two UMOVs per use: ~10 % of all instructions the product kernels executed, and code size
+// in a fetch-bound loop (profiles/).  (Not `const` on the device, so that they are not folded
+// back into immediates; the values and the order of operations are unchanged.)
+#ifdef RB_DEVICE_BUILD
+#define RB_CTABLE __constant__
+#else
+#define RB_CTABLE static const
+#endif
+RB_CTABLE double kMeisselTab[47] = {
+    1.0 / 10321920.0, 860160.0, 1290240.0, 2580480.0,
+    645120.0, 28672.0, 2709504.0, 6547968.0,
+    672000.0, 23224320.0, 18708480.0, 1048320.0,
+    8192.0, 2519040.0, 60518400.0, 151828480.0,
+    61254720.0, 2163168.0, 138700800.0, 800163840.0,
+    940423680.0, 228049920.0, 5537280.0, 6144.0,
+    2644992.0, 299351808.0, 3405435264.0, 8653594320.0,
+    5897669400.0, 954875250.0, 16907985.0, 625766400.0,
+    12841758720.0, 60631119360.0, 86387857920.0, 38435160960.0,
+    4450158720.0, 59968440.0, 0.984023040e9, 0.442810368e9,
+    0.303114240e9, 0.233192960e9, 0.190139040e9, 0.160692840e9,
+    0.139204065e9, 0.1476034560e10, 1.0e-3,
+};
+RB_CTABLE double kDebyeTab[53] = {
+    1.0 / 10321920.0, 810485676000000.0 * kAt4, 19451656224000000.0 * kAt0, 19451656224000000.0 * kAt1,
+    3241942704000000.0 * kAt3, 27016189200000.0 * kAt6, 53603550000.0 * kAt9, 40608750.0 * kAt12,
+    14875.0 * kAt15, 5403237840000.0 * kAt6, 69470200800000.0 * kAt4, 401283384.0 * kAt15,
+    4707059994.0 * kAt13, 3012121710.0 * kAt12, 36011689560.0 * kAt10, 8027667648000.0 * kAt9,
+    8027667648000.0 * kAt7, 1296777081600000.0 * kAt3, 41423013450.0 * kAt12, 484040056500.0 * kAt10,
+    67540473000000.0 * kAt6, 1748257220.0 * kAt15, 19964735910.0 * kAt13, 2594411820000.0 * kAt9,
+    29331862560000.0 * kAt7, 78248884350.0 * kAt12, 860873013000.0 * kAt10, 94556662200000.0 * kAt6,
+    1938419560.0 * kAt15, 20997160275.0 * kAt13, 2283511230000.0 * kAt9, 47153256150.0 * kAt12,
+    459918459000.0 * kAt10, 849093050.0 * kAt15, 8397889500.0 * kAt13, 643242600000.0 * kAt9,
+    11448186750.0 * kAt12, 173573400.0 * kAt15, 1474097625.0 * kAt13, 1161410250.0 * kAt12,
+    17481100.0 * kAt15, 833000.0 * kAt15, kAt7, kAt10,
+    kAt13, 1.0e55, 21612951360000.0, 3859455600000.0,
+    88445857500.0, 5360355000.0, 113704500.0, 3123750.0,
+    0.58354968672000000e17,
+};
+RB_CTABLE double kExpFacTab[9] = {
+    1.0 / 10321920.0, 40320.0, 20160.0, 6720.0,
+    1680.0, 336.0, 56.0, 8.0,
+    690.0,
+};
+
 // bessel.c:22-51
 RB_FN double exp_factor(double f_factor, double f_exp)
 {
@@ -123,11 +169,11 @@ RB_FN double exp_factor(double f_factor, double f_exp)
     if (fabs_exp < 1e-3) {
         const double x = f_exp;
         return f_factor *
-               (1.0 + ((40320.0 + (20160.0 + (6720.0 + (1680.0 + (336.0 + (56.0 + (8.0 + x) * x) * x) * x) * x) * x) * x) * x / 40320.0));
+               (1.0 + ((kExpFacTab[1] + (kExpFacTab[2] + (kExpFacTab[3] + (kExpFacTab[4] + (kExpFacTab[5] + (kExpFacTab[6] + (kExpFacTab[7] + x) * x) * x) * x) * x) * x) * x) * x / kExpFacTab[1]));
     }
     // (one exp call site for the three cases of bessel.c:40-50)
     double mult = f_factor, arg = f_exp;
-    if (fabs_exp > 690.0) {
+    if (fabs_exp > kExpFacTab[8]) {
         const double log_f = rb_log(fabs(f_factor));
         if (log_f * f_exp < 0.0) {
             mult = (f_factor < 0.0) ? -1.0 : 1.0;
@@ -146,21 +192,21 @@ RB_FN double leung_meissel_first(const LeungOrder &o, double x)
     const double Z = sqrt(eps * (1.0 + z));
     const double U = 1.0 / (n * Z * Z * Z);
     const double t1 = z * z;
-    constexpr double D = 1.0 / 10321920.0;
+    const double D = kMeisselTab[0];
 
     // V_n sum, a polynomial in U whose coefficients are polynomials in z^2
-    const double p0 = (860160.0 + 1290240.0 * t1) * D;
-    const double p1 = ((-2580480.0 - 645120.0 * t1) * t1) * D;
-    const double p2 = (-28672.0 + (2709504.0 + (6547968.0 + 672000.0 * t1) * t1) * t1) * D;
-    const double p3 = ((-2580480.0 + (-23224320.0 + (-18708480.0 - 1048320.0 * t1) * t1) * t1) * t1) * D;
+    const double p0 = (kMeisselTab[1] + kMeisselTab[2] * t1) * D;
+    const double p1 = ((-kMeisselTab[3] - kMeisselTab[4] * t1) * t1) * D;
+    const double p2 = (-kMeisselTab[5] + (kMeisselTab[6] + (kMeisselTab[7] + kMeisselTab[8] * t1) * t1) * t1) * D;
+    const double p3 = ((-kMeisselTab[3] + (-kMeisselTab[9] + (-kMeisselTab[10] - kMeisselTab[11] * t1) * t1) * t1) * t1) * D;
     const double p4 =
-        (-8192.0 + (-2519040.0 + (-60518400.0 + (-151828480.0 + (-61254720.0 - 2163168.0 * t1) * t1) * t1) * t1) * t1) * D;
+        (-kMeisselTab[12] + (-kMeisselTab[13] + (-kMeisselTab[14] + (-kMeisselTab[15] + (-kMeisselTab[16] - kMeisselTab[17] * t1) * t1) * t1) * t1) * t1) * D;
     const double p5 =
-        ((2580480.0 + (138700800.0 + (800163840.0 + (940423680.0 + (228049920.0 + 5537280.0 * t1) * t1) * t1) * t1) * t1) * t1) * D;
-    const double p6 = (6144.0 + (-2644992.0 + (-299351808.0 + (-3405435264.0 + (-8653594320.0 + (-5897669400.0 +
-                       (-954875250.0 - 16907985.0 * t1) * t1) * t1) * t1) * t1) * t1) * t1) * D;
-    const double p7 = ((2580480.0 + (625766400.0 + (12841758720.0 + (60631119360.0 + (86387857920.0 + (38435160960.0 +
-                       (4450158720.0 + 59968440.0 * t1) * t1) * t1) * t1) * t1) * t1) * t1) * t1) * D;
+        ((kMeisselTab[3] + (kMeisselTab[18] + (kMeisselTab[19] + (kMeisselTab[20] + (kMeisselTab[21] + kMeisselTab[22] * t1) * t1) * t1) * t1) * t1) * t1) * D;
+    const double p6 = (kMeisselTab[23] + (-kMeisselTab[24] + (-kMeisselTab[25] + (-kMeisselTab[26] + (-kMeisselTab[27] + (-kMeisselTab[28] +
+                       (-kMeisselTab[29] - kMeisselTab[30] * t1) * t1) * t1) * t1) * t1) * t1) * t1) * D;
+    const double p7 = ((kMeisselTab[3] + (kMeisselTab[31] + (kMeisselTab[32] + (kMeisselTab[33] + (kMeisselTab[34] + (kMeisselTab[35] +
+                       (kMeisselTab[36] + kMeisselTab[37] * t1) * t1) * t1) * t1) * t1) * t1) * t1) * t1) * D;
     const double vsum1 = U * (p0 + U * (p1 + U * (p2 + U * (p3 + U * (p4 + U * (p5 + U * (p6 + U * p7)))))));
 
     // "I substitute Gamma(n+1) with (n+1)*Gamma(n) in the denominator" (bessel.c:123)
@@ -169,12 +215,12 @@ RB_FN double leung_meissel_first(const LeungOrder &o, double x)
     double exp_val;
     if (eps < 1e-4 && n > 1e3) {
         const double exp2 = -n * sqrt(2.0 * eps) * eps *
-                            (0.984023040e9 + (0.442810368e9 + (0.303114240e9 + (0.233192960e9 + (0.190139040e9 +
-                             (0.160692840e9 + 0.139204065e9 * eps) * eps) * eps) * eps) * eps) * eps) / 0.1476034560e10;
+                            (kMeisselTab[38] + (kMeisselTab[39] + (kMeisselTab[40] + (kMeisselTab[41] + (kMeisselTab[42] +
+                             (kMeisselTab[43] + kMeisselTab[44] * eps) * eps) * eps) * eps) * eps) * eps) / kMeisselTab[45];
         exp_val = o.c_stirling + exp2 - vsum1;
     } else {
         double inv_zp1;
-        if (Z < 1.0e-3)
+        if (Z < kMeisselTab[46])
             inv_zp1 = 1.0 + (-1.0 + (1.0 + (-1.0 + (1.0 + (-1.0 + (1.0 - Z) * Z) * Z) * Z) * Z) * Z) * Z;
         else
             inv_zp1 = 1.0 / (1.0 + Z);
@@ -217,7 +263,7 @@ RB_FN_NOINLINE double leung_meissel_second(double n, double x)
 // polynomial in ez = x - n whose coefficients are polynomials in x^(1/3).
 RB_FN double leung_debye_eps(double n, double x)
 {
-    if (x > 1.0e55)
+    if (x > kDebyeTab[45])
         return NAN;
 
     const double ez = x - n;
@@ -225,36 +271,36 @@ RB_FN double leung_debye_eps(double n, double x)
     const double t3 = z * z;
     const double t4 = x * z;
     const double t10 = t4 * t4;
-    const double t38 = (810485676000000.0 * kAt4) * t3;
-    const double t70 = kAt7 * t3;
-    const double t93 = kAt10 * t3;
-    const double t107 = kAt13 * t3;
+    const double t38 = kDebyeTab[1] * t3;
+    const double t70 = kDebyeTab[42] * t3;
+    const double t93 = kDebyeTab[43] * t3;
+    const double t107 = kDebyeTab[44] * t3;
     const double t114 = ez * ez;
     const double t146 = t10 * t10;
 
-    const double lead = (-5403237840000.0 * kAt6 + (69470200800000.0 * kAt4 + (19451656224000000.0 * kAt0) * t4) * t3) * t10 * z;
+    const double lead = (-kDebyeTab[9] + (kDebyeTab[10] + kDebyeTab[2] * t4) * t3) * t10 * z;
 
-    const double e0 = -401283384.0 * kAt15 + (4707059994.0 * kAt13 + (3012121710.0 * kAt12 + (-36011689560.0 * kAt10 +
-                      (8027667648000.0 * kAt9 + (-8027667648000.0 * kAt7 + (-1296777081600000.0 * kAt3 +
-                      (19451656224000000.0 * kAt1) * t3) * t4) * t3) * z) * t3) * z) * t3;
-    const double e1 = (-41423013450.0 * kAt12 + (484040056500.0 * kAt10 + (67540473000000.0 * kAt6 - t38) * t4) * t3) * x;
-    const double e2 = 1748257220.0 * kAt15 + (-19964735910.0 * kAt13 + (-2594411820000.0 * kAt9 +
-                      (29331862560000.0 * kAt7 + (3241942704000000.0 * kAt3) * t4) * t3) * t4) * t3;
-    const double e3 = (78248884350.0 * kAt12 + (-860873013000.0 * kAt10 + (-94556662200000.0 * kAt6 + t38) * t4) * t3) * x;
-    const double e4 = -1938419560.0 * kAt15 + (20997160275.0 * kAt13 + (2283511230000.0 * kAt9 - 21612951360000.0 * t70) * t4) * t3;
-    const double e5 = (-47153256150.0 * kAt12 + (459918459000.0 * kAt10 + (27016189200000.0 * kAt6) * t4) * t3) * x;
-    const double e6 = 849093050.0 * kAt15 + (-8397889500.0 * kAt13 + (-643242600000.0 * kAt9 + 3859455600000.0 * t70) * t4) * t3;
-    const double e7 = (11448186750.0 * kAt12 - 88445857500.0 * t93) * x;
-    const double e8 = -173573400.0 * kAt15 + (1474097625.0 * kAt13 + (53603550000.0 * kAt9) * t4) * t3;
-    const double e9 = (-1161410250.0 * kAt12 + 5360355000.0 * t93) * x;
-    const double e10 = -113704500.0 * t107 + 17481100.0 * kAt15;
-    const double e11 = (40608750.0 * kAt12) * x;
-    const double e12 = -833000.0 * kAt15 + 3123750.0 * t107 + (14875.0 * kAt15) * t114;
+    const double e0 = -kDebyeTab[11] + (kDebyeTab[12] + (kDebyeTab[13] + (-kDebyeTab[14] +
+                      (kDebyeTab[15] + (-kDebyeTab[16] + (-kDebyeTab[17] +
+                      kDebyeTab[3] * t3) * t4) * t3) * z) * t3) * z) * t3;
+    const double e1 = (-kDebyeTab[18] + (kDebyeTab[19] + (kDebyeTab[20] - t38) * t4) * t3) * x;
+    const double e2 = kDebyeTab[21] + (-kDebyeTab[22] + (-kDebyeTab[23] +
+                      (kDebyeTab[24] + kDebyeTab[4] * t4) * t3) * t4) * t3;
+    const double e3 = (kDebyeTab[25] + (-kDebyeTab[26] + (-kDebyeTab[27] + t38) * t4) * t3) * x;
+    const double e4 = -kDebyeTab[28] + (kDebyeTab[29] + (kDebyeTab[30] - kDebyeTab[46] * t70) * t4) * t3;
+    const double e5 = (-kDebyeTab[31] + (kDebyeTab[32] + kDebyeTab[5] * t4) * t3) * x;
+    const double e6 = kDebyeTab[33] + (-kDebyeTab[34] + (-kDebyeTab[35] + kDebyeTab[47] * t70) * t4) * t3;
+    const double e7 = (kDebyeTab[36] - kDebyeTab[48] * t93) * x;
+    const double e8 = -kDebyeTab[37] + (kDebyeTab[38] + kDebyeTab[6] * t4) * t3;
+    const double e9 = (-kDebyeTab[39] + kDebyeTab[49] * t93) * x;
+    const double e10 = -kDebyeTab[50] * t107 + kDebyeTab[40];
+    const double e11 = kDebyeTab[7] * x;
+    const double e12 = -kDebyeTab[41] + kDebyeTab[51] * t107 + kDebyeTab[8] * t114;
 
     const double poly = (e0 + (e1 + (e2 + (e3 + (e4 + (e5 + (e6 + (e7 + (e8 + (e9 + (e10 + (e11 + e12 * ez) * ez) * ez) * ez) *
                         ez) * ez) * ez) * ez) * ez) * ez) * ez) * ez) * ez;
 
-    return (lead + poly) / (kPi * t146 * 0.58354968672000000e17);
+    return (lead + poly) / (kPi * t146 * kDebyeTab[52]);
 }
 
 // Integer order 0 <= n < 30 (the reference calls gsl_sf_bessel_Jn,
