@@ -38,11 +38,11 @@ SEED = 20260
 # FP64 floating-point operations executed per 31-node Gauss-Kronrod application (FMA = 2): ncu
 # smsp__sass_thread_inst_executed_op_{dfma,dmul,dadd}_pred_on over one launch of each product
 # kernel divided by the applications that launch counted (profiles/r01_fast_kernels_details.txt and
-# r01_fast_kernels_summary.md: 4096 seeded pitchy power-law points, 38.5 / 145.7 ms).
-FLOP_PER_APPLICATION = {"symphony": 46.6e3, "heyvaerts": 26.15e3}
+# r01_fast_kernels_summary.md: 4096 seeded pitchy power-law points, 32.4 / 106.0 ms).
+FLOP_PER_APPLICATION = {"symphony": 38.06e3, "heyvaerts": 28.38e3}
 # DRAM bytes (read + write) per point of the same captures (register spills to local memory; the
 # algorithmic traffic is ~110 B per point): the path does not touch HBM.
-DRAM_BYTES_PER_POINT = {"symphony": (0.764e6 + 13.78e6) / 4096, "heyvaerts": (1.366e6 + 32.16e6) / 4096}
+DRAM_BYTES_PER_POINT = {"symphony": (1.20e6 + 39.58e6) / 4096, "heyvaerts": (2.52e6 + 43.53e6) / 4096}
 
 
 def parse():
