@@ -56,6 +56,14 @@ def run(name):
         g = np.load(os.path.join(HERE, "symphony_golden.npz"))["table"]
         kind, s, theta = O.POWER_LAW, g[:, 0].copy(), g[:, 1].copy()
         params = [g[:, 2].copy(), 1.0, 1e12, 1e10]
+    elif name == "pitchy_pl_high_s":
+        # BASELINE C4's high-harmonic corner on the power-law side: s in [1e6, 1e7], where the
+        # reference shrinks the gamma window (rel_width, symphony.rs:337-341)
+        rng = np.random.default_rng(SEED + 5)
+        n = 64
+        kind = O.PITCHY_PL
+        s, theta = 10 ** rng.uniform(6, 7, n), rng.uniform(0.05, 1.5, n)
+        params = [rng.uniform(1.8, 4.0, n), rng.uniform(0.0, 3.0, n), 1.0, 1e12, 1e10]
     elif name == "juettner_sweep":
         kind, s, theta, params = synthetic_batch("juettner_sweep", 0)
         sel = np.arange(0, len(s), 37)  # 443 of the 16384 grid points

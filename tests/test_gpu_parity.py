@@ -40,7 +40,7 @@ pytestmark = pytest.mark.gpu
 
 NAMES = R.COEFFICIENT_NAMES
 FIXTURES = ["pitchy_pl", "powerlaw", "pitchy_kappa", "symphony_rows"]
-FAST_FIXTURES = FIXTURES + ["pitchy_pl_4k", "pitchy_kappa_2k"]
+FAST_FIXTURES = FIXTURES + ["pitchy_pl_4k", "pitchy_kappa_2k", "pitchy_pl_high_s"]
 
 
 def run(fx, mode, mask=0xFF, extras=True, **kw):
