@@ -247,7 +247,7 @@ def test_fast_mode_within_the_integration_tolerance(golden, name):
     for c in range(4):  # j_I, alpha_I, j_Q, alpha_Q
         ok = finite_pairs(res.values[c], want[c])
         rel = np.abs(res.values[c][ok] / want[c][ok] - 1)
-        assert (rel <= 1e-3).mean() >= frac, (NAMES[c], (rel <= 1e-3).mean())
+        assert (rel > 1e-3).sum() <= max(1, (1 - frac) * ok.sum()), (NAMES[c], (rel <= 1e-3).mean())
         # the tail of this distribution is the reference's noise, e.g. 1.0e-2 on j_Q at theta = 0.009
         # (pitchy_kappa_2k point 1950) where FAST at 1e-6 tolerances reproduces FAST to 1e-6
         assert rel.max() <= 2e-2, (NAMES[c], rel.max())
@@ -256,7 +256,7 @@ def test_fast_mode_within_the_integration_tolerance(golden, name):
         ok = finite_pairs(res.values[c], want[c])
         scale = np.abs(lobes[lp]) + np.abs(lobes[lm])
         err = np.abs(res.values[c] - want[c])[ok] / scale[ok]
-        assert (err <= 1e-3).mean() >= frac, (NAMES[c], (err <= 1e-3).mean())
+        assert (err > 1e-3).sum() <= max(1, (1 - frac) * ok.sum()), (NAMES[c], (err <= 1e-3).mean())
         assert err.max() <= 5e-3, (NAMES[c], err.max())
         resolved = ok & (np.abs(want[c]) > 1e-2 * scale)
         assert (np.sign(res.values[c][resolved]) == np.sign(want[c][resolved])).all()
@@ -274,7 +274,7 @@ def test_fast_mode_within_the_integration_tolerance(golden, name):
         hi = sigma0 >= 1.0
         ok = finite_pairs(res.values[c], want[c]) & hi
         rel = np.abs(res.values[c][ok] / want[c][ok] - 1)
-        assert (rel <= 1e-3).mean() >= 0.99, (NAMES[c], (rel <= 1e-3).mean())
+        assert (rel > 1e-3).sum() <= max(1, 0.01 * ok.sum()), (NAMES[c], (rel <= 1e-3).mean())
         assert rel.max() <= 2e-2, (NAMES[c], rel.max())
         assert (np.sign(res.values[c][ok]) == np.sign(want[c][ok])).all()
         mismatch = (np.isnan(res.values[c]) != np.isnan(want[c])) & hi
