@@ -160,6 +160,28 @@ int rimphony_b200_compute_dimensionless(int kind, const double *params, int n_pa
 int rimphony_b200_compute_cgs(int kind, const double *params, int n_params, int coeff, int stokes, double nu,
                               double b, double n_e, double theta, double *out);
 
+/* The reference's diagnostics of the Symphony double integral at ONE point
+ * (FullSynchrotronCalculator::diagnostic_symphony_*, src/lib.rs:254-298), evaluated for `count`
+ * arguments at once, one warp each, with the reference's own sequence of rule applications:
+ *   GAMMA_INTEGRAND     out[i] = gamma_integrand(gamma = b[i], n = a[i])   (symphony.rs:398-479, 585-590)
+ *   GAMMA_INTEGRAL      out[i] = G(n = a[i])                               (symphony.rs:312-395, 576-580)
+ *   N_INTEGRAL          out[i] = QAG of G over [a[i], b[i]]; the reference's Err is NaN here
+ *                                                                          (symphony.rs:297-307, 571-574)
+ *   GAMMA_CONTRIBUTION  out[i] = sum over n at gamma = a[i], dimensional constants applied
+ *                                                                          (symphony.rs:481-569, 592-598)
+ * coeff is EMISSION or ABSORPTION.  For Stokes V the gamma integral covers the lobe below
+ * gamma_peak, as in the reference (CalculationState::new, symphony.rs:62).  b may be null for
+ * the one-argument diagnostics; status (nullable) receives RIMPHONY_B200_STATUS_* bits.  Host arrays. */
+enum rimphony_b200_diagnostic {
+    RIMPHONY_B200_DIAG_GAMMA_INTEGRAND = 0,
+    RIMPHONY_B200_DIAG_GAMMA_INTEGRAL = 1,
+    RIMPHONY_B200_DIAG_N_INTEGRAL = 2,
+    RIMPHONY_B200_DIAG_GAMMA_CONTRIBUTION = 3
+};
+int rimphony_b200_diagnostic_symphony(int kind, const double *params, int n_params, int coeff, int stokes, double s,
+                                      double theta, int what, int64_t count, const double *a, const double *b,
+                                      double *out, int32_t *status);
+
 /* The Leung fast Bessel evaluator on the device: j[i] = J_n(x) as pkgw_bessel_j,
  * dj[i] = J_n'(x) as pkgw_bessel_dj (leung-bessel/src/bessel.c:318-405).  Host arrays. */
 int rimphony_b200_bessel_jn(int64_t count, const double *n, const double *x, double *j, double *dj);

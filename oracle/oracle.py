@@ -114,6 +114,8 @@ def lib():
     L.orc_test_qag.restype = i32
     L.orc_test_deriv.argtypes = [i32, dbl, dbl, dbl]
     L.orc_test_deriv.restype = dbl
+    L.orc_symphony_diagnostic.argtypes = [ctypes.POINTER(Dist), i32, i32, dbl, dbl, i32, dbl, dbl]
+    L.orc_symphony_diagnostic.restype = dbl
     L.orc_gk31_tables.argtypes = [_c_double_p, _c_double_p, _c_double_p]
     L.orc_gk31_tables.restype = None
     _lib = L
@@ -132,6 +134,14 @@ def make_dist(kind, params):
 def compute_dimensionless(dist, coeff, stokes, s, theta, stats=None):
     sp = ctypes.byref(stats) if stats is not None else None
     return lib().orc_compute_dimensionless(ctypes.byref(dist), coeff, stokes, s, theta, sp)
+
+
+DIAG_GAMMA_INTEGRAND, DIAG_GAMMA_INTEGRAL, DIAG_N_INTEGRAL, DIAG_GAMMA_CONTRIBUTION = range(4)
+
+
+def symphony_diagnostic(dist, coeff, stokes, s, theta, what, a, b=0.0):
+    """FullSynchrotronCalculator::diagnostic_symphony_* (src/lib.rs:254-298)."""
+    return lib().orc_symphony_diagnostic(ctypes.byref(dist), coeff, stokes, s, theta, what, a, b)
 
 
 def compute_cgs(dist, coeff, stokes, nu, b, n_e, theta):

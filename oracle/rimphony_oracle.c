@@ -275,6 +275,7 @@ typedef struct {
     orc_workspace *gamma_ws;
     orc_stats *stats;
     double cur_n; /* closure variable for the gamma integrand */
+    double cur_gamma; /* closure variable of the gamma-contribution diagnostic */
 } sym_state;
 
 /* src/symphony.rs:398-479 */
@@ -526,6 +527,85 @@ double orc_symphony(const orc_dist *d, int coeff, int stokes, double s, double t
                     orc_stats *stats)
 {
     return orc_symphony_lobes(d, coeff, stokes, s, theta, stats, NULL);
+}
+
+/* The reference's diagnostics of the Symphony double integral (src/lib.rs:254-298):
+ * what = 0 gamma_integrand(gamma = b, n = a)            (symphony.rs:585-590)
+ *        1 gamma_integral(n = a)                        (symphony.rs:391-395, 576-580)
+ *        2 the QAG of gamma_integral over [a, b]; NaN for the reference's Err (symphony.rs:297-307)
+ *        3 gamma_contribution(gamma = a)                (symphony.rs:491-569)
+ * CalculationState::new leaves the Stokes V switch on the negative lobe (symphony.rs:62). */
+static double sym_integrand_of_n(double n, void *ctx)
+{
+    sym_state *st = (sym_state *)ctx;
+    const double gamma = st->cur_gamma;
+    st->cur_n = n;
+    return sym_gamma_integrand(gamma, st);
+}
+
+double orc_symphony_diagnostic(const orc_dist *d, int coeff, int stokes, double s, double theta,
+                               int what, double a, double b)
+{
+    sym_state st;
+    double result = NAN, abserr;
+
+    st.d = d;
+    st.coeff = coeff;
+    st.stokes = stokes;
+    st.s = s;
+    st.cos_observer_angle = cos(theta);
+    st.sin_observer_angle = sin(theta);
+    st.stokes_v_switch = LOBE_NEGATIVE;
+    st.stats = NULL;
+    st.cur_n = NAN;
+    st.cur_gamma = NAN;
+    st.gamma_ws = (orc_workspace *)malloc(sizeof(orc_workspace));
+    orc_workspace_init(st.gamma_ws, 5000);
+
+    if (what == 0) {
+        st.cur_n = a;
+        result = sym_gamma_integrand(b, &st);
+    } else if (what == 1) {
+        result = sym_gamma_integral(a, &st);
+    } else if (what == 2) {
+        orc_workspace *n_ws = (orc_workspace *)malloc(sizeof(orc_workspace));
+        orc_workspace_init(n_ws, 1000);
+        if (orc_qag31(sym_gamma_integral, &st, a, b, 0., 1e-3, n_ws, &result, &abserr) != ORC_SUCCESS)
+            result = NAN;
+        free(n_ws);
+    } else {
+        const double gamma = a;
+        const double delta = fabs(st.cos_observer_angle) * sqrt(gamma * gamma - 1.);
+        const int64_t n_minus = (int64_t)(s * (gamma - delta) + 1.);
+        const int64_t n_plus = (int64_t)(s * (gamma + delta));
+        const int64_t FULLY_DISCRETE_THRESHOLD = 1000, N_DISCRETE = 30;
+        double ans = 0., contrib;
+        int64_t n;
+
+        st.cur_gamma = gamma;
+        if (n_plus - n_minus < FULLY_DISCRETE_THRESHOLD) {
+            for (n = n_minus; n < n_plus + 1; n++)
+                ans += sym_integrand_of_n((double)n, &st);
+        } else {
+            for (n = n_minus; n < n_minus + N_DISCRETE + 1; n++)
+                ans += sym_integrand_of_n((double)n, &st);
+            if (orc_qag31(sym_integrand_of_n, &st, (double)(n_minus + N_DISCRETE + 1), (double)n_plus,
+                          0., 1e-3, st.gamma_ws, &contrib, &abserr) != ORC_SUCCESS)
+                contrib = NAN;
+            ans += contrib;
+        }
+        if (!isfinite(ans))
+            result = NAN;
+        else if (coeff == ORC_COEFF_EMISSION)
+            result = ans * ((ORC_TWO_PI * ORC_ELECTRON_CHARGE) * (ORC_TWO_PI * ORC_ELECTRON_CHARGE) /
+                            (ORC_SPEED_LIGHT * fabs(st.cos_observer_angle)));
+        else
+            result = ans * (-1. * (ORC_TWO_PI * ORC_ELECTRON_CHARGE) * (ORC_TWO_PI * ORC_ELECTRON_CHARGE) /
+                            (2. * ORC_MASS_ELECTRON * ORC_SPEED_LIGHT * fabs(st.cos_observer_angle)));
+    }
+
+    free(st.gamma_ws);
+    return result;
 }
 
 /* ------------------------------------------------------------------------- */

@@ -42,6 +42,8 @@ void orc_calc_f_derivatives(const orc_dist *d, double gamma, double cos_xi, doub
 double orc_symphony(const orc_dist *d, int coeff, int stokes, double s, double theta, orc_stats *stats);
 double orc_symphony_lobes(const orc_dist *d, int coeff, int stokes, double s, double theta,
                           orc_stats *stats, double lobes[2]);
+double orc_symphony_diagnostic(const orc_dist *d, int coeff, int stokes, double s, double theta,
+                               int what, double a, double b);
 double orc_heyvaerts(const orc_dist *d, int stokes, double s, double theta, orc_stats *stats);
 
 double orc_compute_dimensionless(const orc_dist *d, int coeff, int stokes, double s, double theta,

@@ -43,6 +43,7 @@ POWER_LAW, THERMAL_JUETTNER, PITCHY_PL, PITCHY_KAPPA = 0, 1, 2, 3
 MODE_FAST, MODE_FAITHFUL, MODE_FUSED_ALL, MODE_FUSED = 0, 1, 2, 3
 
 STATUS_NAN, STATUS_CAP_HIT, STATUS_NORM_FAILED, STATUS_REROUTED = 1, 2, 4, 8
+DIAG_GAMMA_INTEGRAND, DIAG_GAMMA_INTEGRAL, DIAG_N_INTEGRAL, DIAG_GAMMA_CONTRIBUTION = 0, 1, 2, 3
 
 COEFFICIENT_NAMES = ("j_I", "alpha_I", "j_Q", "alpha_Q", "j_V", "alpha_V", "rho_Q", "rho_V")
 
@@ -321,6 +322,51 @@ class FullSynchrotronCalculator(SynchrotronCalculator):
     def compute_all_dimensionless_batch(self, s, theta, extras=False):
         """The additive batch entry point: returns a ``BatchResult``."""
         return self._batch(np.atleast_1d(np.asarray(s, dtype=np.float64)), theta, 0xFF, extras=extras)
+
+
+    # -- diagnostics of the Symphony double integral (src/lib.rs:249-299) ----------------
+    # Scalar arguments give the reference's scalar; arrays give one value per element (one
+    # warp each).  The distribution must be a single one (scalar parameters).
+
+    def _diagnostic(self, what, coeff, stokes, s, theta, a, b=None):
+        if not self.distrib._is_scalar():
+            raise ValueError("the Symphony diagnostics take a single distribution (scalar parameters)")
+        if Coefficient(coeff) == Coefficient.Faraday:
+            raise ValueError("the Symphony diagnostics are defined for emission and absorption")
+        scalar = np.ndim(a) == 0 and (b is None or np.ndim(b) == 0)
+        if b is None:
+            a_arr = np.ascontiguousarray(np.atleast_1d(a), dtype=np.float64)
+            b_arr = None
+        else:
+            a_b, b_b = np.broadcast_arrays(np.atleast_1d(np.asarray(a, dtype=np.float64)),
+                                           np.atleast_1d(np.asarray(b, dtype=np.float64)))
+            a_arr, b_arr = np.ascontiguousarray(a_b), np.ascontiguousarray(b_b)
+        pv = np.array([float(np.asarray(c).reshape(-1)[0]) for c in self.distrib._columns()], dtype=np.float64)
+        out = np.full(a_arr.shape, np.nan)
+        L = _lib.load()
+        _lib.check(L.rimphony_b200_diagnostic_symphony(
+            self.distrib.KIND, pv.ctypes.data_as(_lib.c_double_p), len(pv), int(coeff), int(stokes), float(s),
+            float(theta), what, a_arr.size, a_arr.ctypes.data_as(_lib.c_double_p),
+            b_arr.ctypes.data_as(_lib.c_double_p) if b_arr is not None else None,
+            out.ctypes.data_as(_lib.c_double_p), None))
+        return float(out.reshape(-1)[0]) if scalar else out
+
+    def diagnostic_symphony_n_integral(self, coeff, stokes, s, theta, n_lo, n_hi):
+        """QAG over n of the gamma integral (lib.rs:254-260).  The reference returns a
+        ``GslResult``; its ``Err`` is NaN here."""
+        return self._diagnostic(DIAG_N_INTEGRAL, coeff, stokes, s, theta, n_lo, n_hi)
+
+    def diagnostic_symphony_gamma_integral(self, coeff, stokes, s, theta, n):
+        """G(n), the gamma integral at harmonic number n (lib.rs:266-272)."""
+        return self._diagnostic(DIAG_GAMMA_INTEGRAL, coeff, stokes, s, theta, n)
+
+    def diagnostic_symphony_gamma_integrand(self, coeff, stokes, s, theta, n, gamma):
+        """The integrand at (n, gamma) (lib.rs:278-284)."""
+        return self._diagnostic(DIAG_GAMMA_INTEGRAND, coeff, stokes, s, theta, n, gamma)
+
+    def diagnostic_symphony_gamma_contribution(self, coeff, stokes, s, theta, gamma):
+        """The double integral sliced the other way: all n at fixed gamma (lib.rs:291-297)."""
+        return self._diagnostic(DIAG_GAMMA_CONTRIBUTION, coeff, stokes, s, theta, gamma)
 
 
 class _PowerLawHighFrequency(SynchrotronCalculator):

@@ -48,6 +48,7 @@ EXPORTED_SYMBOLS = (
     "rimphony_b200_compute_all_dimensionless_multi",
     "rimphony_b200_compute_dimensionless",
     "rimphony_b200_compute_cgs",
+    "rimphony_b200_diagnostic_symphony",
     "rimphony_b200_bessel_jn",
     "rimphony_b200_dist_eval",
     "rimphony_b200_last_kernel_ms",
@@ -85,6 +86,8 @@ def load():
     L.rimphony_b200_compute_all_dimensionless_multi.argtypes = [i32, i64, c_double_p, c_double_p, pp, i32, OP, c_double_p, c_int32_p, i32]
     L.rimphony_b200_compute_dimensionless.argtypes = [i32, c_double_p, i32, i32, i32, dbl, dbl, c_double_p]
     L.rimphony_b200_compute_cgs.argtypes = [i32, c_double_p, i32, i32, i32, dbl, dbl, dbl, dbl, c_double_p]
+    L.rimphony_b200_diagnostic_symphony.argtypes = [i32, c_double_p, i32, i32, i32, dbl, dbl, i32, i64, c_double_p,
+                                                    c_double_p, c_double_p, c_int32_p]
     L.rimphony_b200_bessel_jn.argtypes = [i64, c_double_p, c_double_p, c_double_p, c_double_p]
     L.rimphony_b200_dist_eval.argtypes = [i32, c_double_p, i32, i64, c_double_p, c_double_p, c_double_p]
     L.rimphony_b200_last_kernel_ms.argtypes = [i32, ctypes.POINTER(ctypes.c_float)]

@@ -102,6 +102,38 @@ __global__ void __launch_bounds__(kThreadsPerBlock, FUSED ? 3 : 4) k_symphony(Ba
     }
 }
 
+// diagnostic_symphony_* (lib.rs:254-298): one warp per argument, reference rule sequence.
+template <int KIND>
+__global__ void __launch_bounds__(kThreadsPerBlock, 4) k_symphony_diag(BatchArgs a, DiagArgs g)
+{
+    using WS = SymWorkspace<false, kSymGammaCap, kSymNCap>;
+    extern __shared__ double smem[];
+    const int warp = threadIdx.x >> 5;
+    WS &ws = reinterpret_cast<WS *>(smem)[warp];
+    Warp w;
+    w.init();
+
+    Dist d;
+    double p0;
+    load_dist<KIND>(a, 0, d, p0);
+    d.norm = a.norm[0];
+    const double s = a.s[0], theta = a.theta[0];
+
+    const long long stride = (long long)gridDim.x * kWarpsPerBlock;
+    for (long long i = (long long)blockIdx.x * kWarpsPerBlock + warp; i < g.count; i += stride) {
+        w.status = 0;
+        w.n_apply_lanes = 0;
+        const double v = symphony_diagnostic<KIND, kSymGammaCap, kSymNCap>(w, d, g.coeff, g.stokes, s, theta, g.what,
+                                                                           g.a[i], g.b ? g.b[i] : 0.0, a.eps_gamma,
+                                                                           a.eps_n, ws);
+        if (w.lane == 0) {
+            g.out[i] = v;
+            if (g.status)
+                g.status[i] = (int)(w.status | ((v == v) ? 0u : kStatusNaN));
+        }
+    }
+}
+
 #ifndef RB_FAST_BLOCKS
 #define RB_FAST_BLOCKS 5 // resident CTAs per SM the product kernels are compiled for (96 registers; +5 % over 4)
 #endif
@@ -313,6 +345,22 @@ int stage_symphony(const BatchArgs &a, bool faithful, int sm_count, cudaStream_t
             return 1;
         k_symphony<KIND, true><<<grid, kThreadsPerBlock, smem, st>>>(a);
     }
+    g_launches++;
+    RB_CUDA(cudaGetLastError());
+    return 0;
+}
+
+template <int KIND>
+int stage_symphony_diag(const BatchArgs &a, const DiagArgs &g, int sm_count, cudaStream_t st)
+{
+    int grid = 0;
+    const size_t smem = kWarpsPerBlock * sizeof(SymWorkspace<false, kSymGammaCap, kSymNCap>);
+    if (set_smem(k_symphony_diag<KIND>, smem) || persistent_grid(k_symphony_diag<KIND>, smem, sm_count, &grid))
+        return 1;
+    const long long need = (g.count + kWarpsPerBlock - 1) / kWarpsPerBlock;
+    if (need < grid)
+        grid = (int)need;
+    k_symphony_diag<KIND><<<grid, kThreadsPerBlock, smem, st>>>(a, g);
     g_launches++;
     RB_CUDA(cudaGetLastError());
     return 0;

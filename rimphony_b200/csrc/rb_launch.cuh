@@ -67,6 +67,16 @@ struct BatchArgs {
 
 constexpr int kCostClasses = 3;
 
+// One diagnostic of the Symphony double integral at `count` arguments of ONE point (the
+// point is element 0 of the BatchArgs arrays): lib.rs:254-298.
+struct DiagArgs {
+    int coeff, stokes, what; // what: kDiag* of rb_symphony.cuh
+    long long count;
+    const double *a, *b;     // n / n_lo / gamma, and gamma / n_hi (b may be null)
+    double *out;
+    int *status;             // kStatus* bits per element (nullable)
+};
+
 // ticket -> point index for kernel `which` (0 = Symphony, 1 = Heyvaerts)
 __device__ __forceinline__ long long ordered_point(const BatchArgs &a, int which, long long ticket)
 {
@@ -142,6 +152,8 @@ int stage_symphony(const BatchArgs &a, bool faithful, int sm_count, cudaStream_t
 int stage_classify(const BatchArgs &a, cudaStream_t st);
 template <int KIND>
 int stage_symphony_fast(const BatchArgs &a, int sm_count, cudaStream_t st);
+template <int KIND>
+int stage_symphony_diag(const BatchArgs &a, const DiagArgs &g, int sm_count, cudaStream_t st);
 template <int KIND>
 int stage_heyvaerts(const BatchArgs &a, bool fused, int sm_count, cudaStream_t st);
 template <int KIND>

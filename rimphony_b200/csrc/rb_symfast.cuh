@@ -204,8 +204,9 @@ RB_FN_NOINLINE void sym_gamma_integral(Warp &w, const SymFastCtx<KIND> &cx, doub
     // is beyond any power-law factor (the first harmonics of a large-s point: exponent ~ s sin(theta)).
     // With the exponent at the peak of the gamma range above kNegligibleExponent the whole gamma
     // integral is < e^-200 of the harmonics that make up the coefficient: it is not evaluated.
+    const double eps_peak = (n >= kNJn) ? sym_eps_at<KIND>(cx, n, gamma_peak) : 0.0;
     if (n >= kNJn) {
-        const double x0 = 1.0 - sym_eps_at<KIND>(cx, n, gamma_peak);
+        const double x0 = 1.0 - eps_peak;
         if (x0 > 0.0 && x0 < 1.0) {
             const double th = sqrt((1.0 - x0) * (1.0 + x0));
             const double exponent = 2.0 * n * (rb_log((1.0 + th) / x0) - th);
@@ -230,12 +231,12 @@ RB_FN_NOINLINE void sym_gamma_integral(Warp &w, const SymFastCtx<KIND> &cx, doub
 
     warp_fence();
 #ifdef RB_DEVICE_BUILD
-    if (w.lane == 0)
+    if (w.lane < 2) // orders n and n + 1 side by side
+        leung_prepare(n + (double)w.lane, w.lane ? ws.on1 : ws.on);
+#else
+    leung_prepare(n, ws.on);
+    leung_prepare(n + 1.0, ws.on1);
 #endif
-    {
-        leung_prepare(n, ws.on);
-        leung_prepare(n + 1.0, ws.on1);
-    }
 
     // Seeds.  Central panels [0, +-T] first (they are popped last-in first-out), outer
     // remainders after them.  The reference's J_n switches from the Debye expansion to a
@@ -259,7 +260,7 @@ RB_FN_NOINLINE void sym_gamma_integral(Warp &w, const SymFastCtx<KIND> &cx, doub
         const bool leung = n >= kNJn;
         warp_fence(); // orders prepared by lane 0
         const double lo = ws.on.lo_minus, hi = ws.on.hi_minus;
-        const double eps0 = leung ? sym_eps_at<KIND>(cx, n, gamma_peak) : 0.0;
+        const double eps0 = eps_peak;
 
         // The four cuts at once: lane group g = 2 side + which samples eps(t) at eight points around
         // the quadratic guess t0 = sqrt(2 (target - eps0)) (one evaluation per lane instead of

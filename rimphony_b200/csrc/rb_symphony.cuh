@@ -405,4 +405,99 @@ RB_FN void symphony_tail_faithful(Warp &w, const Dist &dist, double s, double th
     out6[5] = lobes4[2] + lobes4[3];
 }
 
+// ---------------------------------------------------------------------------
+// The reference's diagnostics of the Symphony double integral (lib.rs:254-298), one value
+// each: the integrand at (n, gamma), G(n), the QAG of G over [n_lo, n_hi], and the
+// "other slicing", the sum over n at fixed gamma (symphony.rs:481-569).  Reference
+// sequence of rule applications throughout (these exist to look inside the calculation).
+enum { kDiagGammaIntegrand = 0, kDiagGammaIntegral = 1, kDiagNIntegral = 2, kDiagGammaContribution = 3 };
+
+// gamma_integrand(gamma, n) as a function of n: the closure of symphony.rs:518, 536.
+template <int KIND>
+struct SymIntegrandOfN {
+    const Dist *d;
+    const SymGeometry *g;
+    double gamma;
+    int sel;
+
+    RB_FN void eval(double n, double (&out)[1]) const
+    {
+        SymOrders ord;
+        leung_prepare(n, ord.on);
+        leung_prepare(n + 1.0, ord.on1);
+        SymGammaIntegrand<KIND, 1> f{d, g, &ord, n, sel};
+        f.eval(gamma, out);
+    }
+};
+
+template <int KIND, int GAMMA_CAP, int N_CAP>
+RB_FN double symphony_diagnostic(Warp &w, const Dist &dist, int coeff, int stokes, double s, double theta, int what,
+                                 double a, double b, double epsrel_gamma, double epsrel_n,
+                                 SymWorkspace<false, GAMMA_CAP, N_CAP> &ws)
+{
+    SymGeometry geom;
+    geom.s = s;
+    geom.cos_th = cos(theta);
+    geom.sin_th = sin(theta);
+
+    // CalculationState::new leaves the Stokes V switch on the negative lobe (symphony.rs:62),
+    // and the diagnostics never move it: G(n) of Stokes V is the integral below gamma_peak.
+    const int acc = (stokes == 2) ? 6 + coeff : 2 * stokes + coeff;
+    const int sel = PolicySymphonySplit::val(acc);
+
+    IntervalList<1> glist;
+    glist.bind(ws.gamma_store, GAMMA_CAP);
+    IntervalList<1> nlist;
+    nlist.bind(ws.n_store, N_CAP);
+    double out[1];
+
+    if (what == kDiagGammaIntegrand) { // a = n, b = gamma (symphony.rs:585-590)
+        SymIntegrandOfN<KIND> f{&dist, &geom, b, sel};
+        f.eval(a, out);
+        return out[0];
+    }
+
+    SymGammaIntegral<KIND, false> G{&dist, &geom, &ws.orders, &glist, 1u, acc, epsrel_gamma};
+    if (what == kDiagGammaIntegral) { // a = n (symphony.rs:391-395)
+        G.eval_collective(w, a, out);
+        return out[0];
+    }
+    if (what == kDiagNIntegral) { // [a, b] = [n_lo, n_hi] (symphony.rs:297-307); Err -> NaN here
+        ApplySeq<1, SymGammaIntegral<KIND, false>> ap{G};
+        const double bounds[2] = {a, b};
+        qag_joint<PolicyPlain<1>>(w, ap, 1, bounds, epsrel_n, nlist, 1u, out);
+        return out[0];
+    }
+
+    // a = gamma (symphony.rs:491-569)
+    const double gamma = a;
+    const double delta = fabs(geom.cos_th) * sqrt(gamma * gamma - 1.0);
+    const long long n_minus = (long long)(s * (gamma - delta) + 1.0);
+    const long long n_plus = (long long)(s * (gamma + delta));
+    constexpr long long kFullyDiscrete = 1000, kNDiscrete = 30;
+    SymIntegrandOfN<KIND> f{&dist, &geom, gamma, sel};
+    double ans = 0.0;
+    if (n_plus - n_minus < kFullyDiscrete) {
+        for (long long n = n_minus; n < n_plus + 1; n++) {
+            f.eval((double)n, out);
+            ans += out[0];
+        }
+    } else {
+        for (long long n = n_minus; n < n_minus + kNDiscrete + 1; n++) {
+            f.eval((double)n, out);
+            ans += out[0];
+        }
+        ApplyLanes<1, SymIntegrandOfN<KIND>> ap{f};
+        const double bounds[2] = {(double)(n_minus + kNDiscrete + 1), (double)n_plus};
+        qag_joint<PolicyPlain<1>>(w, ap, 1, bounds, epsrel_n, glist, 1u, out);
+        ans += out[0];
+    }
+    if (!(ans - ans == 0.0))
+        return NAN;
+    const double two_pi_e = kTwoPi * kElectronCharge;
+    const double pre = (coeff == 0) ? two_pi_e * two_pi_e / (kSpeedLight * fabs(geom.cos_th))
+                                    : -1.0 * two_pi_e * two_pi_e / (2.0 * kMassElectron * kSpeedLight * fabs(geom.cos_th));
+    return ans * pre;
+}
+
 } // namespace rb

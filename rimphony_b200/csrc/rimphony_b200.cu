@@ -322,6 +322,14 @@ int launch(DeviceContext &c, int kind, const BatchArgs &a, const ResolvedOptions
     return fail("unknown distribution kind %d", kind);
 }
 
+template <int KIND>
+int diag_kind(DeviceContext &c, const BatchArgs &a, const DiagArgs &g)
+{
+    if (stage_normalize<KIND>(a, c.sm_count, c.stream))
+        return 1;
+    return stage_symphony_diag<KIND>(a, g, c.sm_count, c.stream);
+}
+
 int collect_times(DeviceContext &c)
 {
     float t;
@@ -635,6 +643,84 @@ int rimphony_b200_compute_cgs(int kind, const double *params, int n_params, int 
     if (rimphony_b200_compute_dimensionless(kind, params, n_params, coeff, stokes, nu / nu_c, theta, &val))
         return 1;
     *out = (coeff == RIMPHONY_B200_EMISSION) ? val * n_e * nu : val * n_e / nu;
+    return 0;
+}
+
+int rimphony_b200_diagnostic_symphony(int kind, const double *params, int n_params, int coeff, int stokes, double s,
+                                      double theta, int what, int64_t count, const double *a, const double *b,
+                                      double *out, int32_t *status)
+{
+    if (count < 0 || !params || !a || !out)
+        return fail("bad arguments");
+    if (coeff < 0 || coeff > 1 || stokes < 0 || stokes > 2)
+        return fail("bad coefficient/stokes selector (the Symphony diagnostics take emission or absorption)");
+    if (what < 0 || what > 3)
+        return fail("unknown diagnostic %d", what);
+    if ((what == RIMPHONY_B200_DIAG_GAMMA_INTEGRAND || what == RIMPHONY_B200_DIAG_N_INTEGRAL) && !b)
+        return fail("this diagnostic takes two argument arrays");
+    if (check_params(kind, n_params))
+        return 1;
+    if (count == 0)
+        return 0;
+    DeviceContext *cp = nullptr;
+    if (get_context(-1, &cp))
+        return 1;
+    DeviceContext &c = *cp;
+    std::lock_guard<std::mutex> guard(c.lock);
+    RB_CUDA(cudaSetDevice(c.device));
+
+    // device staging: [s | theta | params | norm | a | b] in, [out | status] out
+    const size_t head = 2 + (size_t)n_params + 1;
+    if (c.in.reserve((head + 2 * (size_t)count) * sizeof(double)) ||
+        c.out.reserve((size_t)count * (sizeof(double) + sizeof(int32_t))))
+        return 1;
+    double host_head[2 + kMaxParams];
+    host_head[0] = s;
+    host_head[1] = theta;
+    for (int j = 0; j < n_params; j++)
+        host_head[2 + j] = params[j];
+    double *d_in = static_cast<double *>(c.in.ptr);
+    RB_CUDA(cudaMemcpyAsync(d_in, host_head, (2 + (size_t)n_params) * sizeof(double), cudaMemcpyHostToDevice, c.stream));
+    double *d_a = d_in + head, *d_b = d_a + count;
+    RB_CUDA(cudaMemcpyAsync(d_a, a, (size_t)count * sizeof(double), cudaMemcpyHostToDevice, c.stream));
+    if (b)
+        RB_CUDA(cudaMemcpyAsync(d_b, b, (size_t)count * sizeof(double), cudaMemcpyHostToDevice, c.stream));
+    double *d_out = static_cast<double *>(c.out.ptr);
+    int32_t *d_status = reinterpret_cast<int32_t *>(d_out + count);
+
+    BatchArgs ba;
+    memset(&ba, 0, sizeof ba);
+    ba.n = 1;
+    ba.s = d_in;
+    ba.theta = d_in + 1;
+    for (int j = 0; j < n_params; j++)
+        ba.params[j] = d_in + 2 + j;
+    ba.n_params = n_params;
+    ba.norm = d_in + 2 + n_params;
+    ba.eps_gamma = ba.eps_n = 1e-3;
+    DiagArgs g{coeff, stokes, what, (long long)count, d_a, b ? d_b : nullptr, d_out, d_status};
+
+    int rc;
+    switch (kind) {
+    case RIMPHONY_B200_POWER_LAW:
+        rc = diag_kind<kDistPowerLaw>(c, ba, g);
+        break;
+    case RIMPHONY_B200_THERMAL_JUETTNER:
+        rc = diag_kind<kDistThermalJuettner>(c, ba, g);
+        break;
+    case RIMPHONY_B200_PITCHY_PL:
+        rc = diag_kind<kDistPitchyPL>(c, ba, g);
+        break;
+    default:
+        rc = diag_kind<kDistPitchyKappa>(c, ba, g);
+        break;
+    }
+    if (rc)
+        return 1;
+    RB_CUDA(cudaMemcpyAsync(out, d_out, (size_t)count * sizeof(double), cudaMemcpyDeviceToHost, c.stream));
+    if (status)
+        RB_CUDA(cudaMemcpyAsync(status, d_status, (size_t)count * sizeof(int32_t), cudaMemcpyDeviceToHost, c.stream));
+    RB_CUDA(cudaStreamSynchronize(c.stream));
     return 0;
 }
 

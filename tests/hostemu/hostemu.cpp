@@ -218,3 +218,32 @@ void emu_dist_eval(int kind, const double *params, int n_params, double gamma, d
 }
 
 } // extern "C"
+
+template <int KIND>
+static double diag_kind(const double *params, int n_params, int coeff, int stokes, double s, double theta, int what,
+                        double a, double b)
+{
+    Dist d;
+    unsigned status = 0;
+    if (make_dist<KIND>(params, n_params, d, status) != 0)
+        return NAN;
+    constexpr int GC = 1024, NC = 1024;
+    auto *ws = new SymWorkspace<false, GC, NC>();
+    Warp w;
+    w.init();
+    const double v = symphony_diagnostic<KIND, GC, NC>(w, d, coeff, stokes, s, theta, what, a, b, 1e-3, 1e-3, *ws);
+    delete ws;
+    return v;
+}
+
+extern "C" double emu_symphony_diag(int kind, const double *params, int n_params, int coeff, int stokes, double s,
+                                    double theta, int what, double a, double b)
+{
+    switch (kind) {
+    case kDistPowerLaw: return diag_kind<kDistPowerLaw>(params, n_params, coeff, stokes, s, theta, what, a, b);
+    case kDistThermalJuettner: return diag_kind<kDistThermalJuettner>(params, n_params, coeff, stokes, s, theta, what, a, b);
+    case kDistPitchyPL: return diag_kind<kDistPitchyPL>(params, n_params, coeff, stokes, s, theta, what, a, b);
+    case kDistPitchyKappa: return diag_kind<kDistPitchyKappa>(params, n_params, coeff, stokes, s, theta, what, a, b);
+    }
+    return NAN;
+}

@@ -98,6 +98,15 @@ def test_bad_arguments_are_infrastructure_errors():
     assert L.rimphony_b200_compute_all_dimensionless(R.POWER_LAW, -1, s, s, cols, 1, None, out, None) != 0
     # an empty batch is a successful no-op, with or without a device
     assert L.rimphony_b200_compute_all_dimensionless(R.POWER_LAW, 0, s, s, cols, 1, None, out, None) == 0
+    # diagnostics: Faraday is not a Symphony coefficient; two-argument diagnostics need both arrays
+    p = (ctypes.c_double * 1)(2.5)
+    assert L.rimphony_b200_diagnostic_symphony(R.POWER_LAW, p, 1, 2, 0, 10.0, 0.5, 1, 1, s, None, out, None) != 0
+    assert L.rimphony_b200_diagnostic_symphony(R.POWER_LAW, p, 1, 0, 0, 10.0, 0.5, 0, 1, s, None, out, None) != 0
+    assert L.rimphony_b200_diagnostic_symphony(R.POWER_LAW, p, 1, 0, 0, 10.0, 0.5, 9, 1, s, s, out, None) != 0
+    assert L.rimphony_b200_diagnostic_symphony(R.POWER_LAW, p, 1, 0, 0, 10.0, 0.5, 1, 0, s, None, out, None) == 0
+    with pytest.raises(ValueError):
+        R.PowerLawDistribution(2.5).full_calculation().diagnostic_symphony_gamma_integral(
+            R.Coefficient.Faraday, R.Stokes.Q, 10.0, 0.5, 40.0)
 
 
 def test_output_slots_follow_lib_rs():

@@ -352,6 +352,67 @@ def test_live_oracle_on_seeded_points(oracle):
     assert np.abs(got[ok] / want[ok] - 1).max() < 1e-6
 
 
+# --- diagnostics of the Symphony double integral (src/lib.rs:249-299) --------------------------
+
+@pytest.mark.parametrize("make,okind,params", [
+    (lambda: R.PitchyPowerLawDistribution(2.5, 1.0), "PITCHY_PL", [2.5, 1.0]),
+    (lambda: R.PowerLawDistribution(3.0), "POWER_LAW", [3.0]),
+    (lambda: R.PitchyKappaDistribution(3.5, 5.0, 1.2), "PITCHY_KAPPA", [3.5, 5.0, 1.2]),
+    (lambda: R.ThermalJuettnerDistribution(10.0), "THERMAL_JUETTNER", [10.0]),
+])
+def test_symphony_diagnostics_match_the_oracle(oracle, make, okind, params):
+    """diagnostic_symphony_{gamma_integrand, gamma_integral, n_integral, gamma_contribution}: the device
+    performs the reference's sequence of rule applications, so it agrees with the oracle to rounding
+    (amplified where J_n' = n J_n / z - J_{n+1} cancels)."""
+    calc = make().full_calculation()
+    d = oracle.make_dist(getattr(oracle, okind), params)
+    rng = np.random.default_rng(5)
+    bad = []
+    for s, theta in ((50.0, 0.9), (3.0, 0.3), (2e6, 1.2)):
+        n0 = s * math.sin(theta)
+        n = n0 * 10 ** rng.uniform(0.02, 4.0, 24) + 31.0  # from the first harmonics to far up the tail
+        # gamma around the peak of the integrand: the window of symphony.rs:315-323, narrowed like n^-1/3
+        peak = (n / s) / math.sin(theta) ** 2
+        half = abs(math.cos(theta)) * np.sqrt((n / s) ** 2 - math.sin(theta) ** 2) / math.sin(theta) ** 2
+        gamma = peak + half * np.minimum(1.0, 2.6 * n ** (-1 / 3)) * rng.uniform(-1, 1, 24)
+        n_hi = n * (1.0 + rng.random(24))
+        g_fixed = np.array([1.5, 2.0, 7.0, 40.0, 300.0, 2e3, 3e4])
+        for coeff in (R.Coefficient.Emission, R.Coefficient.Absorption):
+            for stokes in (R.Stokes.I, R.Stokes.Q, R.Stokes.V):
+                cases = [
+                    (calc.diagnostic_symphony_gamma_integrand(coeff, stokes, s, theta, n, gamma),
+                     [oracle.symphony_diagnostic(d, coeff, stokes, s, theta, oracle.DIAG_GAMMA_INTEGRAND, a, b)
+                      for a, b in zip(n, gamma)], 1e-9),
+                    (calc.diagnostic_symphony_gamma_integral(coeff, stokes, s, theta, n),
+                     [oracle.symphony_diagnostic(d, coeff, stokes, s, theta, oracle.DIAG_GAMMA_INTEGRAL, a) for a in n],
+                     1e-6),
+                    (calc.diagnostic_symphony_n_integral(coeff, stokes, s, theta, n[:6], n_hi[:6]),
+                     [oracle.symphony_diagnostic(d, coeff, stokes, s, theta, oracle.DIAG_N_INTEGRAL, a, b)
+                      for a, b in zip(n[:6], n_hi[:6])], 1e-6),
+                    (calc.diagnostic_symphony_gamma_contribution(coeff, stokes, s, theta, g_fixed),
+                     [oracle.symphony_diagnostic(d, coeff, stokes, s, theta, oracle.DIAG_GAMMA_CONTRIBUTION, g)
+                      for g in g_fixed], 1e-6),
+                ]
+                for which, (got, want, tol) in enumerate(cases):
+                    want = np.asarray(want)
+                    # J_n carries ~n ulp of rounding in both implementations (see the Bessel test above)
+                    tol = tol if s < 1e3 else max(tol, 1e-5) * 10
+                    where = (okind, s, int(coeff), int(stokes), which)
+                    if not np.array_equal(np.isnan(got), np.isnan(want)):
+                        bad.append(where + ("nan pattern", got, want))
+                        continue
+                    ok = ~np.isnan(want) & (want != 0)
+                    zero = ~ok & ~np.isnan(want)
+                    if not np.array_equal(got[zero], want[zero]):
+                        bad.append(where + ("zeros",))
+                    if ok.any() and not np.abs(got[ok] / want[ok] - 1).max() < tol:
+                        bad.append(where + (float(np.abs(got[ok] / want[ok] - 1).max()), tol))
+    assert not bad, bad
+    # scalar arguments give the reference's scalar
+    v = calc.diagnostic_symphony_gamma_integral(R.Coefficient.Emission, R.Stokes.I, 50.0, 0.9, 75.0)
+    assert isinstance(v, float)
+
+
 # --- known answers through the reference-shaped API ------------------------------------------
 
 def test_one_powerlaw_direct():

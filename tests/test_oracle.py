@@ -191,3 +191,52 @@ def test_live_oracle_reproduces_fixture(oracle, golden):
     out, lobes = oracle.batch(fx["kind"], fx["s"][rows], fx["theta"][rows], [p[rows] for p in fx["params"]])
     assert np.allclose(out, fx["out"][:, rows], rtol=1e-12, atol=0.0, equal_nan=True)
     assert np.allclose(lobes, fx["lobes"][:, rows], rtol=1e-12, atol=0.0, equal_nan=True)
+
+
+# --- diagnostics of the Symphony double integral (src/lib.rs:249-299) ------------------------
+
+def test_symphony_diagnostics_are_mutually_consistent(oracle):
+    """The four diagnostic_symphony_* restatements against each other and against an
+    independent quadrature: G(n) is the integral of the integrand over the gamma window of
+    symphony.rs:315-366 (Stokes V: the lobe below gamma_peak, the state CalculationState::new
+    leaves, symphony.rs:62), the n integral is the integral of G, and the fully discrete
+    gamma contribution is the plain sum over n times the dimensional constants."""
+    O = oracle
+    d = O.make_dist(O.PITCHY_PL, [2.5, 1.0])
+    s, theta = 50.0, 0.9
+    n = 75.0
+    nos, sn, cs = n / s, math.sin(theta), abs(math.cos(theta))
+    root = math.sqrt(nos * nos - sn * sn)
+    g_minus, g_plus = (nos - cs * root) / sn**2, (nos + cs * root) / sn**2
+    g_peak = 0.5 * (g_minus + g_plus)
+    for coeff in (O.EMISSION, O.ABSORPTION):
+        for stokes, lo, hi in ((O.STOKES_I, g_minus, g_plus), (O.STOKES_Q, g_minus, g_plus), (O.STOKES_V, g_minus, g_peak)):
+            f = lambda g: O.symphony_diagnostic(d, coeff, stokes, s, theta, O.DIAG_GAMMA_INTEGRAND, n, g)  # noqa: E731
+            want, _ = scipy.integrate.quad(f, lo, hi, epsrel=1e-8, limit=200)
+            got = O.symphony_diagnostic(d, coeff, stokes, s, theta, O.DIAG_GAMMA_INTEGRAL, n)
+            assert abs(got / want - 1) < 2e-3, (coeff, stokes, got, want)
+
+    G = lambda x: O.symphony_diagnostic(d, O.EMISSION, O.STOKES_I, s, theta, O.DIAG_GAMMA_INTEGRAL, x)  # noqa: E731
+    want, _ = scipy.integrate.quad(G, 80.0, 200.0, epsrel=1e-6, limit=200)
+    got = O.symphony_diagnostic(d, O.EMISSION, O.STOKES_I, s, theta, O.DIAG_N_INTEGRAL, 80.0, 200.0)
+    assert abs(got / want - 1) < 2e-3
+
+    gamma = 2.0  # n_plus - n_minus < 1000: fully discrete (symphony.rs:508-514)
+    delta = cs * math.sqrt(gamma * gamma - 1)
+    n_minus, n_plus = int(s * (gamma - delta) + 1), int(s * (gamma + delta))
+    total = 0.0
+    for k in range(n_minus, n_plus + 1):
+        total += O.symphony_diagnostic(d, O.EMISSION, O.STOKES_I, s, theta, O.DIAG_GAMMA_INTEGRAND, float(k), gamma)
+    pre = (2 * math.pi * 4.80320680e-10) ** 2 / (2.99792458e10 * cs)
+    got = O.symphony_diagnostic(d, O.EMISSION, O.STOKES_I, s, theta, O.DIAG_GAMMA_CONTRIBUTION, gamma)
+    assert abs(got / (total * pre) - 1) < 1e-6
+    # the partially discrete branch (30 harmonics + a QAG over n) is the same sum to the QAG tolerance
+    gamma = 40.0
+    delta = cs * math.sqrt(gamma * gamma - 1)
+    n_minus, n_plus = int(s * (gamma - delta) + 1), int(s * (gamma + delta))
+    assert n_plus - n_minus >= 1000
+    ks = np.arange(n_minus, n_plus + 1, dtype=np.float64)
+    total = sum(O.symphony_diagnostic(d, O.ABSORPTION, O.STOKES_Q, s, theta, O.DIAG_GAMMA_INTEGRAND, k, gamma) for k in ks)
+    pre = -(2 * math.pi * 4.80320680e-10) ** 2 / (2 * 9.1093826e-28 * 2.99792458e10 * cs)
+    got = O.symphony_diagnostic(d, O.ABSORPTION, O.STOKES_Q, s, theta, O.DIAG_GAMMA_CONTRIBUTION, gamma)
+    assert abs(got / (total * pre) - 1) < 5e-3
