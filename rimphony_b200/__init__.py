@@ -263,7 +263,12 @@ class SynchrotronCalculator:
         return val * n_e / nu
 
     def compute_all_dimensionless(self, s, theta):
-        raise NotImplementedError
+        # the provided method of the trait (lib.rs:178-191): [j_I, alpha_I, j_Q, alpha_Q, j_V, alpha_V, rho_Q, rho_V]
+        order = [(Coefficient.Emission, Stokes.I), (Coefficient.Absorption, Stokes.I), (Coefficient.Emission, Stokes.Q),
+                 (Coefficient.Absorption, Stokes.Q), (Coefficient.Emission, Stokes.V), (Coefficient.Absorption, Stokes.V),
+                 (Coefficient.Faraday, Stokes.Q), (Coefficient.Faraday, Stokes.V)]
+        return np.stack([np.asarray(self.compute_dimensionless(c, st, s, theta), dtype=np.float64) for c, st in order],
+                        axis=-1)
 
     def compute_all_cgs(self, nu, b, n_e, theta):
         # lib.rs:196-209
