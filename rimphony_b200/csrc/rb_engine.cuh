@@ -167,14 +167,13 @@ RB_FN void tile_store(double *tile, const Warp &w, int node, const double (&vals
     }
 }
 
-// --- several small panels in one application --------------------------------------------
-// The 32 lanes of one application can also carry two 15-point or four 7-point Kronrod panels
-// (lanes 0-14 / 16-30, resp. lanes 8p..8p+6 of quarter p; the remaining lanes have weight 0).
-// The tile and the quarter-row sums of the reduction do not care which rule a lane belongs to:
-// a lane stores its pre-weighted values, a quarter (or a pair of quarters) is one panel.
-// Per-lane abscissa and weights of the two layouts; read with the lane as index, so they live
-// in global memory (L1-cached) rather than in the constant bank, which serialises divergent
-// indices.
+// --- two panels in one application --------------------------------------------------------
+// The 32 lanes of one application can also carry two 15-point Kronrod panels (lanes 0-14 and
+// 16-30; lanes 15 and 31 have weight 0).  The tile and the quarter-row sums of the reduction do
+// not care which rule a lane belongs to: a lane stores its pre-weighted values, a pair of
+// quarters is one panel.  Per-lane abscissa and weights of that layout; read with the lane as
+// index, so they live in global memory (L1-cached) rather than in the constant bank, which
+// serialises divergent indices.
 #ifdef RB_DEVICE_BUILD
 #define RB_LANE_TABLE static __device__ const
 #else
@@ -182,7 +181,6 @@ RB_FN void tile_store(double *tile, const Warp &w, int node, const double (&vals
 #endif
 
 #define RB_K15_ROW(T) T(0), T(1), T(2), T(3), T(4), T(5), T(6), T(7), T(8), T(9), T(10), T(11), T(12), T(13), T(14), 0.0
-#define RB_K7_ROW(T) T(0), T(1), T(2), T(3), T(4), T(5), T(6), 0.0
 
 // the literal values (the RB_TABLE copies above are __constant__ and cannot initialise these)
 #define RB_K15X(i) ((i) == 7 ? 0.0 : ((i) < 7 ? -1.0 : 1.0) * \
@@ -199,19 +197,10 @@ RB_FN void tile_store(double *tile, const Warp &w, int node, const double (&vals
     ((i) == 1 || (i) == 13 ? 0.129484966168869693270611432679082 : (i) == 3 || (i) == 11 ? 0.279705391489276667901467771423780 : \
      (i) == 5 || (i) == 9 ? 0.381830050505118944950369775488975 : 0.0))
 #define RB_K15WD(i) (RB_K15WK(i) - RB_K15WG(i))
-#define RB_K7X(i) ((i) == 3 ? 0.0 : ((i) < 3 ? -1.0 : 1.0) * \
-    ((i) == 0 || (i) == 6 ? 0.9604912687080202834235071 : (i) == 1 || (i) == 5 ? 0.7745966692414833770358531 : 0.4342437493468025580020715))
-#define RB_K7WK(i) ((i) == 3 ? 0.4509165386584741423451101 : \
-    ((i) == 0 || (i) == 6 ? 0.1046562260264672651938239 : (i) == 1 || (i) == 5 ? 0.2684880898683334407285693 : 0.4013974147759622229050518))
-#define RB_K7WG(i) ((i) == 3 ? 0.8888888888888888888888889 : ((i) == 1 || (i) == 5 ? 0.5555555555555555555555556 : 0.0))
-#define RB_K7WD(i) (RB_K7WK(i) - RB_K7WG(i))
 
 RB_LANE_TABLE double L15_X[32] = {RB_K15_ROW(RB_K15X), RB_K15_ROW(RB_K15X)};
 RB_LANE_TABLE double L15_WK[32] = {RB_K15_ROW(RB_K15WK), RB_K15_ROW(RB_K15WK)};
 RB_LANE_TABLE double L15_WD[32] = {RB_K15_ROW(RB_K15WD), RB_K15_ROW(RB_K15WD)};
-RB_LANE_TABLE double L7_X[32] = {RB_K7_ROW(RB_K7X), RB_K7_ROW(RB_K7X), RB_K7_ROW(RB_K7X), RB_K7_ROW(RB_K7X)};
-RB_LANE_TABLE double L7_WK[32] = {RB_K7_ROW(RB_K7WK), RB_K7_ROW(RB_K7WK), RB_K7_ROW(RB_K7WK), RB_K7_ROW(RB_K7WK)};
-RB_LANE_TABLE double L7_WD[32] = {RB_K7_ROW(RB_K7WD), RB_K7_ROW(RB_K7WD), RB_K7_ROW(RB_K7WD), RB_K7_ROW(RB_K7WD)};
 
 // Store the node values of lane `lane` with explicit weights (multi-panel layouts).
 template <int NV>
@@ -239,10 +228,10 @@ RB_FN double quad_error(double d, double a, double hl)
     return (min_err > err) ? min_err : err;
 }
 
-// Reduce a tile that holds `npart` (2 or 4) panels of half-lengths hl[p]: every lane of channel
-// c's group ends up with the estimates r[p], e[p] of all the panels of its channel.
-RB_FN_NOINLINE void tile_reduce_parts(const double *tile, int nv, int npart, const double (&hl)[4],
-                                      PerChan<double> (&r)[4], PerChan<double> (&e)[4])
+// Reduce a tile that holds two 15-point panels (columns of quarters 0-1 and 2-3) of half-lengths
+// hl0, hl1: per channel the estimates (r0, e0) and (r1, e1) of the two panels.
+RB_FN_NOINLINE void tile_reduce_pair(const double *tile, int nv, double hl0, double hl1, PerChan<double> &r0,
+                                     PerChan<double> &e0, PerChan<double> &r1, PerChan<double> &e1)
 {
 #ifdef RB_DEVICE_BUILD
     const int lane = threadIdx.x & 31;
@@ -259,28 +248,24 @@ RB_FN_NOINLINE void tile_reduce_parts(const double *tile, int nv, int npart, con
             d += rb[t];
         }
     }
-    if (npart == 2) {
-        k += __shfl_xor_sync(0xffffffffu, k, 1);
-        d += __shfl_xor_sync(0xffffffffu, d, 1);
-        a += __shfl_xor_sync(0xffffffffu, a, 1);
-    }
-    const int my_part = (npart == 2) ? (q >> 1) : q;
-    const double my_hl = hl[my_part];
+    k += __shfl_xor_sync(0xffffffffu, k, 1);
+    d += __shfl_xor_sync(0xffffffffu, d, 1);
+    a += __shfl_xor_sync(0xffffffffu, a, 1);
+    const bool second = (q & 2) != 0;
+    const double my_hl = second ? hl1 : hl0;
     const double my_r = k * my_hl;
     const double my_e = quad_error(d, a, my_hl);
-    const int step = 4 / npart;
-#pragma unroll
-    for (int p = 0; p < 4; p++) {
-        const int src = (lane & ~3) + ((p < npart) ? p * step : 0);
-        r[p].v = __shfl_sync(0xffffffffu, my_r, src);
-        e[p].v = __shfl_sync(0xffffffffu, my_e, src);
-    }
+    const double ot_r = __shfl_xor_sync(0xffffffffu, my_r, 2);
+    const double ot_e = __shfl_xor_sync(0xffffffffu, my_e, 2);
+    r0.v = second ? ot_r : my_r;
+    e0.v = second ? ot_e : my_e;
+    r1.v = second ? my_r : ot_r;
+    e1.v = second ? my_e : ot_e;
 #else
-    const int per = 4 / npart; // quarters per panel
     for (int c = 0; c < nv; c++) {
-        for (int p = 0; p < npart; p++) {
+        for (int p = 0; p < 2; p++) {
             double k = 0.0, d = 0.0, a = 0.0;
-            for (int q = p * per; q < (p + 1) * per; q++) {
+            for (int q = 2 * p; q < 2 * p + 2; q++) {
                 double kq = 0.0, dq = 0.0, aq = 0.0;
                 for (int t = 0; t < 8; t++) {
                     const double va = tile[c * kEngRow + 9 * q + t];
@@ -292,8 +277,9 @@ RB_FN_NOINLINE void tile_reduce_parts(const double *tile, int nv, int npart, con
                 d += dq;
                 a += aq;
             }
-            r[p].v[c] = k * hl[p];
-            e[p].v[c] = quad_error(d, a, hl[p]);
+            const double hl = p ? hl1 : hl0;
+            (p ? r1 : r0).v[c] = k * hl;
+            (p ? e1 : e0).v[c] = quad_error(d, a, hl);
         }
     }
 #endif

@@ -29,6 +29,8 @@
 namespace rb {
 
 constexpr double kPeakSpan = 2.6;    // seed half-width in units of n^(-1/3): exp(-(2/3) 2.6^3) = 8e-6, tail beyond < 1e-6
+constexpr double kGrade = 0.875;     // low n: the central panels are cut again at this fraction of the first cut
+constexpr double kUncutSplit = 0.5;  // a side without cuts is seeded as two panels, split at this fraction of the span
 constexpr double kInnerFloor = 1.0; // acceptance floor of a gamma panel, fraction of the integral so far
 constexpr double kPanelWidth = 2.302585092994046; // outer panel width in u = ln n (one decade)
 constexpr int kMaxChunks = 400;   // safety net of the chunk loop (the reference has none)
@@ -131,15 +133,9 @@ RB_FN_NOINLINE double sym_eps_at(const SymFastCtx<KIND> &cx, double n, double ga
     return (n - sym_bessel_arg<KIND>(cx, n, gamma, b_, c_, s_)) / n;
 }
 
-// The six gamma integrands at one node (symphony.rs:398-479).  Out of line: it is the body of
-// both the shared-application pass and the 31-point loop, and the kernel is fetch-bound.
+// The six gamma integrands at one node (symphony.rs:398-479); one call site.
 template <int KIND>
-#ifdef RB_SYM_SHARED_APPLICATIONS
-RB_FN_NOINLINE void sym_node( // two call sites: keep one copy
-#else
-RB_FN void sym_node(
-#endif
-const SymFastCtx<KIND> &cx, double n, double gamma, double (&out)[6])
+RB_FN void sym_node(const SymFastCtx<KIND> &cx, double n, double gamma, double (&out)[6])
 {
     const double costh = cx.cos_th, sinth = cx.sin_th;
     double beta, cos_xi, sin_xi;
@@ -374,181 +370,121 @@ RB_FN_NOINLINE void sym_gamma_integral(Warp &w, const SymFastCtx<KIND> &cx, doub
         big[c] = 0.0;
     }
 
-    // The usual case at n >~ 2000: three smooth panels per side and no remainders.  They are
-    // small enough for lower-order rules, so they share applications: the two central panels
-    // as two 15-point Kronrod rules (lanes 0-14, 16-30), then the four blend / tail panels
-    // (~1 % of the integral) as four 7-point rules (one per quarter of the warp).  A panel that
-    // misses its tolerance goes to the stack and gets the regular 31-point treatment below.
-    // EXPERIMENT, off by default (-DRB_SYM_SHARED_APPLICATIONS): rule applications per point drop
-    // from 1023 to 646, but on the B200 the kernel gets SLOWER (1221 ms vs 1003 ms at 131 072
-    // points): a shared application runs every Bessel branch (Debye, blend, Meissel) in one warp
-    // instead of one branch per panel, and the extra per-panel bookkeeping is warp-uniform code.
-#ifdef RB_SYM_SHARED_APPLICATIONS
-    const bool six_panels = cut[0][0] > 0.0 && cut[0][0] < cut[0][1] && cut[0][1] < span && cut[1][0] > 0.0 &&
-                            cut[1][0] < cut[1][1] && cut[1][1] < span;
-#else
-    const bool six_panels = false;
-#endif
-    // a third shared application (two 15-point rules) takes the outer remainders while they are kept
-    const int n_pass = keep_remainders ? 3 : 2;
-    if (six_panels) {
-#pragma unroll 1
-        for (int pass = 0; pass < n_pass; pass++) {
-            const int npart = (pass == 1) ? 4 : 2;
-            // panel p of this pass: [pa[p], pb[p]], side ps[p]
-            double pa[4], pb[4];
-            int ps[4];
-            if (pass == 0) {
-                pa[0] = -cut[0][0], pb[0] = 0.0, ps[0] = 0;
-                pa[1] = 0.0, pb[1] = cut[1][0], ps[1] = 1;
-                pa[2] = pa[3] = pb[2] = pb[3] = 0.0, ps[2] = ps[3] = 0;
-            } else if (pass == 2) {
-                pa[0] = -1.0, pb[0] = -span, ps[0] = 0;
-                pa[1] = span, pb[1] = 1.0, ps[1] = 1;
-                pa[2] = pa[3] = pb[2] = pb[3] = 0.0, ps[2] = ps[3] = 0;
-            } else {
-                pa[0] = -span, pb[0] = -cut[0][1], ps[0] = 0;
-                pa[1] = -cut[0][1], pb[1] = -cut[0][0], ps[1] = 0;
-                pa[2] = cut[1][0], pb[2] = cut[1][1], ps[2] = 1;
-                pa[3] = cut[1][1], pb[3] = span, ps[3] = 1;
-            }
-            double hl[4];
-#pragma unroll
-            for (int p = 0; p < 4; p++)
-                hl[p] = 0.5 * (pb[p] - pa[p]) * half;
-            warp_fence(); // previous reads of the tile are done
-#ifdef RB_DEVICE_BUILD
-            {
-                const int l = w.lane;
-                const bool k7 = (pass == 1);
-                const int p = k7 ? (l >> 3) : (l >> 4);
-                const double x = k7 ? L7_X[l] : L15_X[l];
-                const double wk = k7 ? L7_WK[l] : L15_WK[l];
-                const double wd = k7 ? L7_WD[l] : L15_WD[l];
-                double vals[6];
-                sym_node<KIND>(cx, n, gamma_peak + half * (0.5 * (pa[p] + pb[p]) + 0.5 * (pb[p] - pa[p]) * x), vals);
-                tile_store_weighted<6>(ws.inner.tile, l, wk, wd, vals);
-            }
-#else
-            for (int l = 0; l < 32; l++) {
-                const bool k7 = (pass == 1);
-                const int p = k7 ? (l >> 3) : (l >> 4);
-                const double x = k7 ? L7_X[l] : L15_X[l];
-                const double wk = k7 ? L7_WK[l] : L15_WK[l];
-                const double wd = k7 ? L7_WD[l] : L15_WD[l];
-                double vals[6];
-                sym_node<KIND>(cx, n, gamma_peak + half * (0.5 * (pa[p] + pb[p]) + 0.5 * (pb[p] - pa[p]) * x), vals);
-                tile_store_weighted<6>(ws.inner.tile, l, wk, wd, vals);
-            }
-#endif
-            w.n_apply_lanes++;
-            warp_fence();
-
-            PerChan<double> pr[4], pe[4];
-            tile_reduce_parts(ws.inner.tile, 6, npart, hl, pr, pe);
-#pragma unroll 1
-            for (int p = 0; p < npart; p++) {
-                PerChan<bool> ok;
-                RB_FOR_CHAN(c, kEngChan) { ok[c] = true; }
-                RB_FOR_CHAN(c, 6)
-                {
-                    big[c] = fmax(big[c], fabs(pr[p][c]));
-                    ok[c] = panel_ok(pr[p][c], pe[p][c], cx.epsrel_gamma, kInnerFloor * fmax(est[c] + fabs(pr[p][c]), big[c]));
-                }
-                if (chan_all(ok, 6)) {
-                    RB_FOR_CHAN(c, 6)
-                    {
-                        est[c] += fabs(pr[p][c]);
-                        if (ps[p])
-                            sum_r[c] += pr[p][c];
-                        else
-                            sum_l[c] += pr[p][c];
-                    }
-                } else {
-#ifdef RB_TRACE_MULTI
-                    RB_TRACE_MULTI(n, pass, p, pr[p], pe[p], est, big);
-#endif
-                    stk.push(w, pa[p], pb[p], ps[p]);
-                }
-            }
-        }
-    } else {
-        if (keep_remainders) {
-            stk.push(w, -1.0, -span, 0);
-            stk.push(w, span, 1.0, 1);
-        }
+    // Seeds, pushed so that they are popped in like pairs: the two central panels first (they fix
+    // the scale `big`), then the two blend panels, the two tails, the two remainders.  Both panels
+    // of such a pair run the same Bessel branch (Debye / both / Meissel, bessel.c:346-357), so a
+    // paired application costs what one of them would alone.
+    if (keep_remainders) {
+        stk.push(w, -1.0, -span, 0);
+        stk.push(w, span, 1.0, 1);
+    }
+    const bool graded = full || keep_remainders;
+    if (graded) {
 #pragma unroll 1
         for (int side = 0; side < 2; side++) {
-            // panels [0, c0], [c0, c1], [c1, span]; empty ones are skipped
+            const double c0 = cut[side][0];
+            if (c0 < span)
+                stk.push(w, side ? kGrade * c0 : -c0, side ? c0 : -kGrade * c0, side);
+        }
+    }
+#pragma unroll 1
+    for (int which = 0; which < 3; which++) {
+#pragma unroll 1
+        for (int side = 0; side < 2; side++) {
+            // panels [c1, span], [c0, c1], [0, c0]; empty ones are skipped
             const double c0 = cut[side][0], c1 = cut[side][1];
-            if (span > c1)
-                stk.push(w, side ? c1 : -span, side ? span : -c1, side);
-            if (c1 > c0)
-                stk.push(w, side ? c0 : -c1, side ? c1 : -c0, side);
-            stk.push(w, side ? 0.0 : -c0, side ? c0 : 0.0, side);
+            double lo = (which == 0) ? c1 : ((which == 1) ? c0 : 0.0);
+            double hi = (which == 0) ? span : ((which == 1) ? c1 : c0);
+            if (!(c0 < span)) { // no cut on this side: two halves instead of one wide panel
+                lo = (which == 0) ? span : ((which == 1) ? kUncutSplit * span : 0.0);
+                hi = (which == 0) ? span : ((which == 1) ? span : kUncutSplit * span);
+            }
+            if (graded && which == 2 && c0 < span)
+                hi = kGrade * c0;
+            if (hi > lo)
+                stk.push(w, side ? lo : -hi, side ? hi : -lo, side);
         }
     }
     stk.seal();
 
+    // Every application carries TWO panels as 15-point Kronrod rules, one per half warp (lanes
+    // 0-14 and 16-30; lanes 15 and 31 have weight zero): the two topmost panels of the stack, or
+    // the two halves of the last one.  The seeds are smooth by construction, so the 15-point
+    // rule meets the tolerance on most of them at once and the number of applications per gamma
+    // integral halves; a panel that misses its tolerance is bisected and its halves form the
+    // next pair.
     while (stk.sp > 0) {
-        double ta, tb;
-        int side;
-        stk.pop(ta, tb, side);
-        const double tc = 0.5 * (ta + tb), thl = 0.5 * (tb - ta);
+        double ta0, tb0, ta1, tb1;
+        int side0, side1;
+        stk.pop(ta0, tb0, side0);
+        if (stk.sp > 0) {
+            stk.pop(ta1, tb1, side1);
+        } else {
+            const double mid = 0.5 * (ta0 + tb0);
+            ta1 = mid, tb1 = tb0, side1 = side0;
+            tb0 = mid;
+        }
         warp_fence(); // the previous reduce has finished reading the tile
 
 #ifdef RB_DEVICE_BUILD
         {
+            const bool second = (w.lane & 16) != 0;
+            const double pa = second ? ta1 : ta0, pb = second ? tb1 : tb0;
+            const double x = L15_X[w.lane], wk = L15_WK[w.lane], wd = L15_WD[w.lane];
             double vals[6];
-            sym_node<KIND>(cx, n, gamma_peak + half * (tc + thl * w.xk), vals);
-            tile_store<6>(ws.inner.tile, w, w.lane, vals);
+            sym_node<KIND>(cx, n, gamma_peak + half * (0.5 * (pa + pb) + 0.5 * (pb - pa) * x), vals);
+            tile_store_weighted<6>(ws.inner.tile, w.lane, wk, wd, vals);
         }
 #else
         for (int l = 0; l < 32; l++) {
+            const bool second = (l & 16) != 0;
+            const double pa = second ? ta1 : ta0, pb = second ? tb1 : tb0;
             double vals[6];
-            sym_node<KIND>(cx, n, gamma_peak + half * (tc + thl * LANE_X[l]), vals);
-            tile_store<6>(ws.inner.tile, w, l, vals);
+            sym_node<KIND>(cx, n, gamma_peak + half * (0.5 * (pa + pb) + 0.5 * (pb - pa) * L15_X[l]), vals);
+            tile_store_weighted<6>(ws.inner.tile, l, L15_WK[l], L15_WD[l], vals);
         }
 #endif
         w.n_apply_lanes++;
         warp_fence();
 
-        PerChan<double> r, e;
-        tile_reduce(ws.inner.tile, 6, thl * half, r, e);
+        PerChan<double> r0, e0, r1, e1;
+        tile_reduce_pair(ws.inner.tile, 6, 0.5 * (tb0 - ta0) * half, 0.5 * (tb1 - ta1) * half, r0, e0, r1, e1);
 
-        PerChan<bool> ok;
-        RB_FOR_CHAN(c, kEngChan) { ok[c] = true; }
-        RB_FOR_CHAN(c, 6)
-        {
-            big[c] = fmax(big[c], fabs(r[c]));
-            ok[c] = panel_ok(r[c], e[c], cx.epsrel_gamma, kInnerFloor * fmax(est[c] + fabs(r[c]), big[c]));
-        }
-        const bool accept = chan_all(ok, 6);
-#ifdef RB_TRACE_INNER
-        RB_TRACE_INNER(n, ta, tb, r, e, ok, est);
-#endif
-        if (accept || !stk.room(2) || panel_too_small(ta, tb) || w.n_apply_lanes > kAppBudget) {
-            if (!accept && w.n_apply_lanes > kAppBudget)
-                w.status |= kStatusCapHit; // (a panel at the bisection floor is an integrable end-point singularity)
+#pragma unroll
+        for (int p = 0; p < 2; p++) {
+            const PerChan<double> &r = p ? r1 : r0;
+            const PerChan<double> &e = p ? e1 : e0;
+            const double ta = p ? ta1 : ta0, tb = p ? tb1 : tb0;
+            const int side = p ? side1 : side0;
+            PerChan<bool> ok;
+            RB_FOR_CHAN(c, kEngChan) { ok[c] = true; }
             RB_FOR_CHAN(c, 6)
             {
-                est[c] += fabs(r[c]);
-                if (side)
-                    sum_r[c] += r[c];
-                else
-                    sum_l[c] += r[c];
+                big[c] = fmax(big[c], fabs(r[c]));
+                ok[c] = panel_ok(r[c], e[c], cx.epsrel_gamma, kInnerFloor * fmax(est[c] + fabs(r[c]), big[c]));
             }
-        } else {
-            // the half nearer the peak (t = 0) is popped first
-            if (side) {
-                stk.push(w, tc, tb, side);
-                stk.push(w, ta, tc, side);
+            const bool accept = chan_all(ok, 6);
+#ifdef RB_TRACE_INNER
+            RB_TRACE_INNER(n, ta, tb, r, e, ok, est);
+#endif
+            if (accept || !stk.room(2) || panel_too_small(ta, tb) || w.n_apply_lanes > kAppBudget) {
+                if (!accept && w.n_apply_lanes > kAppBudget)
+                    w.status |= kStatusCapHit; // (a panel at the bisection floor is an integrable end-point singularity)
+                RB_FOR_CHAN(c, 6)
+                {
+                    est[c] += fabs(r[c]);
+                    if (side)
+                        sum_r[c] += r[c];
+                    else
+                        sum_l[c] += r[c];
+                }
             } else {
+                const double tc = 0.5 * (ta + tb);
                 stk.push(w, ta, tc, side);
                 stk.push(w, tc, tb, side);
             }
-            stk.seal();
         }
+        stk.seal();
     }
 
 #ifdef RB_TRACE_GEND
