@@ -190,8 +190,10 @@ RB_FN_NOINLINE void hey_inner_integral(Warp &w, const HeyFastCtx<KIND> &cx, int 
             } else {
                 HeyQRIntegrand<KIND, 2> f{cx.d, &g, v, 0};
                 if (sine_map) {
-                    const double jac = sine_amp * cos(t); // = x, exactly
-                    f.eval(sine_amp * sin(t), vals, jac);
+                    double sin_t, cos_t;
+                    sincos(t, &sin_t, &cos_t);
+                    const double jac = sine_amp * cos_t; // = x, exactly
+                    f.eval(sine_amp * sin_t, vals, jac);
                     vals[0] *= jac;
                     vals[1] *= jac;
                 } else
@@ -214,8 +216,10 @@ RB_FN_NOINLINE void hey_inner_integral(Warp &w, const HeyFastCtx<KIND> &cx, int 
             } else {
                 HeyQRIntegrand<KIND, 2> f{cx.d, &g, v, 0};
                 if (sine_map) {
-                    const double jac = sine_amp * cos(t); // = x, exactly
-                    f.eval(sine_amp * sin(t), vals, jac);
+                    double sin_t, cos_t;
+                    sincos(t, &sin_t, &cos_t);
+                    const double jac = sine_amp * cos_t; // = x, exactly
+                    f.eval(sine_amp * sin_t, vals, jac);
                     vals[0] *= jac;
                     vals[1] *= jac;
                 } else
@@ -519,9 +523,19 @@ RB_FN void heyvaerts_point_fast(Warp &w, const Dist &dist, double s, double thet
     }
     RB_FOR_CHAN(c, 2) { alive[c] = true; }
 
+    // The QR part first (heyvaerts.rs:156-185; the two parts are independent sums): where the
+    // calculation fails it is almost always here (the QR domain of a point with s <= 3 touches
+    // gamma = 1), and a channel that is NaN needs no NR part.
+    const double s15 = kInverseSqrt3 * sigma0 * sqrt(sigma0);
+    const double sigma_low = sigma0 > s15 ? sigma0 : s15;
+    hey_march<KIND>(w, cx, kHeyQR, sigma_low, sigma0, +1, true, 1e6 * sigma0, qr_val, alive);
+    PerChan<bool> dead;
+    RB_FOR_CHAN(c, kEngChan) { dead[c] = !alive[c]; }
+    const bool skip_nr = chan_all(dead, kEngChan);
+
     // the central NR integral over [-3 sigma0, 3 sigma0] (heyvaerts.rs:97), cut at 0 and at
     // the edges of the empty region sigma_min <= 3
-    {
+    if (!skip_nr) {
         const double p3 = 3.0 * sigma0;
         const double hole = (sigma0 < 3.0) ? sqrt(9.0 - cx.g.sigma0_sq) : 0.0;
         if (p3 > hole) {
@@ -541,10 +555,6 @@ RB_FN void heyvaerts_point_fast(Warp &w, const Dist &dist, double s, double thet
     const double p3 = 3.0 * sigma0;
     hey_march<KIND>(w, cx, kHeyNR, p3, p3, +1, true, INFINITY, nr_val, alive);
     hey_march<KIND>(w, cx, kHeyNR, -p3, p3, -1, false, INFINITY, nr_val, alive);
-
-    const double s15 = kInverseSqrt3 * sigma0 * sqrt(sigma0);
-    const double sigma_low = sigma0 > s15 ? sigma0 : s15;
-    hey_march<KIND>(w, cx, kHeyQR, sigma_low, sigma0, +1, true, 1e6 * sigma0, qr_val, alive);
 
     const double scale = 2.0 * kElectronCharge * kElectronCharge / (kMassElectron * (s * cx.g.sin_th) * (s * cx.g.sin_th));
     PerChan<double> total;
