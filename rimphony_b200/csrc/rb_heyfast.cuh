@@ -57,8 +57,11 @@ enum { kMapLinear = 0, kMapLog = 1, kMapNegLog = 2, kMapSqrt = 3 };
 
 // One inner integral (both channels) at the outer node `v` (pomega for NR, sigma for
 // QR), multiplied by wa / wb and parked in column `col` of the outer tile.
+// Returns true when the integral is NaN in both channels (a NaN node value: the integrand is
+// inf - inf where gamma = 1, see the note above); the caller's result is NaN then, whatever
+// the other nodes hold.
 template <int KIND>
-RB_FN_NOINLINE void hey_inner_integral(Warp &w, const HeyFastCtx<KIND> &cx, int which, double v, int col, double wa,
+RB_FN_NOINLINE bool hey_inner_integral(Warp &w, const HeyFastCtx<KIND> &cx, int which, double v, int col, double wa,
                                        double wb)
 {
     HeyFastWS &ws = *cx.ws;
@@ -169,6 +172,7 @@ RB_FN_NOINLINE void hey_inner_integral(Warp &w, const HeyFastCtx<KIND> &cx, int 
         big[c] = 0.0;
     }
 
+    bool all_nan = false;
     while (!empty && stk.sp > 0) {
         double ta, tb;
         int tag;
@@ -253,6 +257,15 @@ RB_FN_NOINLINE void hey_inner_integral(Warp &w, const HeyFastCtx<KIND> &cx, int 
                 est[c] += fabs(r[c]);
                 sum[c] += r[c];
             }
+            // an accepted NaN panel makes the sum NaN: nothing is left to integrate once that
+            // holds for both channels
+            PerChan<bool> gone;
+            RB_FOR_CHAN(c, kEngChan) { gone[c] = true; }
+            RB_FOR_CHAN(c, 2) { gone[c] = !(sum[c] == sum[c]); }
+            if (chan_all(gone, 2)) {
+                all_nan = true;
+                break;
+            }
         } else {
             stk.push(w, tc, tb, 0);
             stk.push(w, ta, tc, 0);
@@ -271,6 +284,7 @@ RB_FN_NOINLINE void hey_inner_integral(Warp &w, const HeyFastCtx<KIND> &cx, int 
             ot[(kEngChan + c) * kEngRow + col] = wb * sum[c];
         }
     }
+    return all_nan;
 }
 
 // The outer integral of one step: both channels over v in [v_lo, v_hi] (same sign, or any
@@ -360,7 +374,11 @@ RB_FN_NOINLINE void hey_outer_integral(Warp &w, const HeyFastCtx<KIND> &cx, int 
                 jac = rb_exp(t);
                 v = (map == kMapLog) ? jac : -jac;
             }
-            hey_inner_integral<KIND>(w, cx, which, v, tile_col(j), rwk[j] * jac, rwd[j] * jac);
+            if (hey_inner_integral<KIND>(w, cx, which, v, tile_col(j), rwk[j] * jac, rwd[j] * jac)) {
+                // both channels NaN at this node: so is the panel, and with it the whole integral
+                RB_FOR_CHAN(c, 2) { result[c] = NAN; }
+                return;
+            }
         }
         warp_fence();
         PerChan<double> r, e;
