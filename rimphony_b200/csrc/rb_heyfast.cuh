@@ -28,7 +28,8 @@
 namespace rb {
 
 constexpr double kHeyInnerFloor = 1.0;
-constexpr double kHeyPanelWidth = 2.0; // widest panel in the log of the variable
+constexpr double kHeyInnerWidth = 4.0; // widest NR inner seed panel in t = arccosh(sigma / sigma_min)
+constexpr double kHeyPanelWidth = 2.0; // widest outer panel in the log of the variable
 constexpr double kHeyDerivStep = 1e-4; // relative step of the derivative probe
 constexpr int kHeyOuterMaxDepth = 13;  // bisections below a seed after which an outer panel is declared divergent
 
@@ -89,7 +90,7 @@ RB_FN_NOINLINE bool hey_inner_integral(Warp &w, const HeyFastCtx<KIND> &cx, int 
             nr_sigma_min = sigma_min;
             const double ratio = sigma_max / sigma_min;
             const double t_lo = 0.0, t_hi = rb_log(ratio + sqrt((ratio - 1.0) * (ratio + 1.0)));
-            int n_seed = (int)ceil((t_hi - t_lo) / kHeyPanelWidth);
+            int n_seed = (int)ceil((t_hi - t_lo) / kHeyInnerWidth);
             n_seed = n_seed < 1 ? 1 : (n_seed > 8 ? 8 : n_seed);
             for (int k = n_seed - 1; k >= 0; k--) // the lowest panel (largest values) is popped first
                 stk.push(w, t_lo + (t_hi - t_lo) * k / n_seed, (k + 1 == n_seed) ? t_hi : t_lo + (t_hi - t_lo) * (k + 1) / n_seed, 0);
