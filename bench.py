@@ -35,15 +35,16 @@ METRIC = "8-coefficient sets/sec"
 UNIT = "coefficient-sets/s"
 SEED = 20260
 
-# FP64 floating-point operations executed per 31-node Gauss-Kronrod application (FMA = 2): ncu
-# smsp__sass_thread_inst_executed_op_{dfma,dmul,dadd}_pred_on over one launch of each product
-# kernel divided by the applications that launch counted (profiles/r01_fast_kernels_details.txt and
-# r01_fast_kernels_summary.md: 4096 seeded pitchy power-law points, 32.4 / 106.0 ms).
-FLOP_PER_APPLICATION = {"symphony": 38.06e3, "heyvaerts": 28.38e3}
+# FP64 floating-point operations executed per Gauss-Kronrod application (one pass of the 32 lanes
+# over 31 nodes, or over two 15-node panels in the Symphony gamma integral; FMA = 2): the
+# predicated-on thread counts of DFMA, DMUL and DADD on the SASS page of one ncu --set full launch
+# of each product kernel, divided by the applications that launch counted
+# (profiles/r01_fast_kernels_details.txt and r01_fast_kernels_summary.md: 4096 seeded pitchy
+# power-law points, 24.7 / 97.4 ms).
+FLOP_PER_APPLICATION = {"symphony": 39.27e3, "heyvaerts": 28.55e3}
 # DRAM bytes (read + write) per point of the same captures (register spills to local memory; the
 # algorithmic traffic is ~110 B per point): the path does not touch HBM.
-DRAM_BYTES_PER_POINT = {"symphony": (1.20e6 + 39.58e6) / 4096, "heyvaerts": (2.52e6 + 43.53e6) / 4096}
-
+DRAM_BYTES_PER_POINT = {"symphony": (1.06e6 + 47.48e6) / 4096, "heyvaerts": (2.42e6 + 37.82e6) / 4096}
 
 def parse():
     ap = argparse.ArgumentParser()
