@@ -474,6 +474,35 @@ def test_empty_single_and_ragged_batches():
         assert np.array_equal(part, full[:, :n], equal_nan=True)
 
 
+def test_degenerate_arguments_end_in_nan_and_leave_their_neighbours_alone():
+    """NaN, infinite, zero and negative s / theta / parameters, theta = 0, pi/2, pi: the kernels terminate
+    (application budget, chunk and step limits), the affected slots are NaN with STATUS_NAN set -- numerical
+    failure is never an infrastructure error (symphony.rs:115-146, heyvaerts.rs:98-177) -- and the regular
+    points interleaved with them come out as in a batch of their own."""
+    kind, s, theta, params = R.synthetic_batch("pitchy_pl", 24, seed=5)
+    params = [np.array(np.broadcast_to(p, s.shape), dtype=np.float64) for p in params]
+    clean = R.compute_all_dimensionless_batch(kind, s, theta, params).values
+    bad_s = {0: np.nan, 3: np.inf, 6: 0.0, 9: -1.0}
+    bad_theta = {1: np.nan, 4: 0.0, 7: math.pi / 2, 10: math.pi, 13: -0.5}
+    s2, th2, par2 = s.copy(), theta.copy(), [p.copy() for p in params]
+    for i, v in bad_s.items():
+        s2[i] = v
+    for i, v in bad_theta.items():
+        th2[i] = v
+    par2[0][15] = np.nan   # p
+    par2[1][18] = np.inf   # k
+    touched = sorted(set(bad_s) | set(bad_theta) | {15, 18})
+    res = R.compute_all_dimensionless_batch(kind, s2, th2, par2)
+    rest = np.setdiff1d(np.arange(len(s)), touched)
+    assert np.array_equal(res.values[:, rest], clean[:, rest], equal_nan=True)
+    for i in (0, 1, 3, 6, 15):   # nothing can be computed from these
+        assert np.isnan(res.values[:, i]).all() and (res.status[i] & (R.STATUS_NAN | R.STATUS_NORM_FAILED))
+    for i in touched:            # every slot is either a number or NaN-with-status, never garbage
+        bad = np.isnan(res.values[:, i])
+        assert not bad.any() or (res.status[i] & (R.STATUS_NAN | R.STATUS_NORM_FAILED))
+        assert np.isfinite(res.values[:, i][~bad]).all()
+
+
 def test_results_do_not_depend_on_batch_order_or_composition():
     """Points are independent: any permutation or split of the batch gives bitwise the same values,
     and so does running it twice (no races in the shared-memory interval lists)."""
