@@ -12,14 +12,16 @@
 //   * the gamma integral is seeded where the integrand lives.  For large n the
 //     integrand is a peak of relative half-width ~ n^(-1/3) around gamma_peak:
 //     with gamma = gamma_peak + t (gamma_+ - gamma_peak), z/n = 1 - t^2/2 - ... and
-//     J_n(z)^2 ~ rb_exp(-(2n/3) |t|^3).  The seeds are [-T, 0], [0, T] with
-//     T = kPeakSpan n^(-1/3) plus the two outer remainders, instead of the
-//     reference's bisection cascade from the full [gamma_-, gamma_+] (15-45 rule
-//     applications per gamma integral at n >= 1e3, measured);
-//   * the integral over continuous n marches in u = ln n with panels of fixed
-//     width in u (n G(n) is a smooth bump in u: exponential rise, power-law
-//     decay), instead of linear chunks grown x10 with a derivative probe each;
-//     it stops by the reference's rule |chunk| < |sum| / 1e5 (symphony.rs:225).
+//     J_n(z)^2 ~ rb_exp(-(2n/3) |t|^3).  The seeds cover [-T, T], T = kPeakSpan n^(-1/3), cut
+//     where the reference's J_n switches expansion (Debye / blend / Meissel), plus the two outer
+//     remainders while T is not yet small, instead of the reference's bisection cascade from the
+//     full [gamma_-, gamma_+] (15-45 rule applications per gamma integral at n >= 1e3, measured);
+//     they are evaluated two per application as 15-point Kronrod rules (rb_engine.cuh);
+//   * the integral over continuous n keeps the reference's chunks [n_start, n_start + delta_n],
+//     growth rules and stop rule |chunk| < |sum| / 1e5 (symphony.rs:196-295) -- where the loop
+//     ends is part of the result -- but integrates each chunk in u = ln n (n G(n) is a smooth
+//     bump in u) with the sequential 15- and 7-point rules, and probes dG/dn by a central
+//     difference.
 #pragma once
 
 #include "rb_bessel.cuh"
