@@ -514,6 +514,100 @@ RB_FN_NOINLINE void sym_gamma_integral(Warp &w, const SymFastCtx<KIND> &cx, doub
     }
 }
 
+// Where G(n) is not smooth in n.  At the peak of the gamma window eps = (n - z)/n falls like
+// n0^2 / (2 n^2) (n0 = s sin(theta)) while the thresholds at which pkgw_bessel_j switches
+// Meissel -> blend -> Debye fall like n^(-2/3) (bessel.c:341-357): at n_a ~ (n0^2 / (2 10^B))^(3/4)
+// the peak enters the blend zone, 23 % further up the Debye zone, and J_{n+1} does the same 1 %
+// apart from J_n.  G(n) has a (n - n_a)^(3/2) onset at each of the four places, and between the
+// two of a pair J_n' = n J_n / z - J_{n+1} mixes two expansions: a bump of ~1e-3 in G that the
+// outer rule otherwise chases down to panels of 3 % width.  The four places are found here (one
+// root each of eps_peak(n) - threshold(n + d), eight lanes per root, two passes) and the outer
+// panels are cut at them.  kink[] is ascending; entries that do not exist are +inf.
+template <int KIND>
+RB_FN void sym_find_kinks(Warp &w, const SymFastCtx<KIND> &cx, double (&kink)[4])
+{
+    const double n0 = cx.s * fabs(cx.sin_th);
+    const double sin2 = cx.sin_th * cx.sin_th;
+    double found[4];
+#ifdef RB_DEVICE_BUILD
+    const int grp = w.lane >> 3, j = w.lane & 7;
+#else
+    for (int grp = 0; grp < 4; grp++) {
+#endif
+        const double shift = (double)(grp & 1);                      // order n or n + 1
+        const double thr = (grp & 2) ? kTenMinusA : kTenMinusB;      // blend -> Debye, Meissel -> blend
+        const double est = rb_exp(0.75 * rb_log(n0 * n0 / (2.0 * thr)));
+        double lo = est * 0.7, hi = est * 1.4;
+        double root = INFINITY;
+        bool ok = est > 1.02 * n0 && est == est;
+#pragma unroll 1
+        for (int pass = 0; pass < 2; pass++) {
+            const double ratio = rb_log(hi / lo) / 7.0;
+#ifdef RB_DEVICE_BUILD
+            const double nj = lo * rb_exp(ratio * j);
+            double fj = NAN;
+            if (ok && nj > n0 * (1.0 + 1e-9) && nj >= kNJn) {
+                const double e = sym_eps_at<KIND>(cx, nj, (nj / cx.s) / sin2);
+                fj = (shift + nj * e) / (nj + shift) - thr * rb_exp(kEtaSlope * rb_log(nj + shift));
+            }
+            const unsigned pos = (__ballot_sync(0xffffffffu, fj > 0.0) >> (8 * grp)) & 0xffu;
+            const unsigned neg = (__ballot_sync(0xffffffffu, fj < 0.0) >> (8 * grp)) & 0xffu;
+            const int cnt = __popc(pos);
+            ok = ok && cnt >= 1 && cnt <= 7 && pos == ((1u << cnt) - 1u) && neg == (0xffu & ~pos);
+            const int src = 8 * grp + (ok ? cnt - 1 : 0);
+            const double fa = __shfl_sync(0xffffffffu, fj, src), na = __shfl_sync(0xffffffffu, nj, src);
+            const double fb = __shfl_sync(0xffffffffu, fj, src + 1), nb = __shfl_sync(0xffffffffu, nj, src + 1);
+#else
+            double fv[8], nv[8];
+            int cnt = 0;
+            bool mono = true;
+            for (int j = 0; j < 8; j++) {
+                nv[j] = lo * rb_exp(ratio * j);
+                fv[j] = NAN;
+                if (ok && nv[j] > n0 * (1.0 + 1e-9) && nv[j] >= kNJn) {
+                    const double e = sym_eps_at<KIND>(cx, nv[j], (nv[j] / cx.s) / sin2);
+                    fv[j] = (shift + nv[j] * e) / (nv[j] + shift) - thr * rb_exp(kEtaSlope * rb_log(nv[j] + shift));
+                }
+                if (fv[j] > 0.0) {
+                    if (cnt != j)
+                        mono = false;
+                    cnt++;
+                } else if (!(fv[j] < 0.0))
+                    mono = false;
+            }
+            ok = ok && mono && cnt >= 1 && cnt <= 7;
+            const double fa = fv[ok ? cnt - 1 : 0], na = nv[ok ? cnt - 1 : 0];
+            const double fb = fv[ok ? cnt : 1], nb = nv[ok ? cnt : 1];
+#endif
+            if (ok) {
+                lo = na;
+                hi = nb;
+                // linear interpolation in ln n
+                root = na * rb_exp(rb_log(nb / na) * (fa / (fa - fb)));
+            }
+        }
+#ifdef RB_DEVICE_BUILD
+    const double mine = ok ? root : INFINITY;
+#pragma unroll
+    for (int g = 0; g < 4; g++)
+        found[g] = __shfl_sync(0xffffffffu, mine, 8 * g);
+#else
+        found[grp] = ok ? root : INFINITY;
+    }
+#endif
+    // ascending (four values: a fixed network)
+#define RB_SWAP_IF(a, b) do { if (found[a] > found[b]) { const double t_ = found[a]; found[a] = found[b]; found[b] = t_; } } while (0)
+    RB_SWAP_IF(0, 1);
+    RB_SWAP_IF(2, 3);
+    RB_SWAP_IF(0, 2);
+    RB_SWAP_IF(1, 3);
+    RB_SWAP_IF(1, 2);
+#undef RB_SWAP_IF
+#pragma unroll
+    for (int g = 0; g < 4; g++)
+        kink[g] = found[g];
+}
+
 // All six j/alpha coefficients of one point, dimensionless (lib.rs:178-191);
 // out6 = j_I, a_I, j_Q, a_Q, j_V, a_V; lobes4 = j_V(+), j_V(-), a_V(+), a_V(-).
 template <int KIND>
@@ -570,6 +664,8 @@ RB_FN void symphony_point_fast(Warp &w, const Dist &dist, double s, double theta
     }
     constexpr double kDerivTol = 1e-5, kDerivStep = 1e-3;
     PanelStack stk;
+    double kink[4];
+    sym_find_kinks<KIND>(w, cx, kink);
 
     bool have_snap = false;
 #ifdef RB_DEVICE_BUILD
@@ -644,14 +740,31 @@ RB_FN void symphony_point_fast(Warp &w, const Dist &dist, double s, double theta
 
         // the chunk, cut into panels of at most kPanelWidth in u; the rightmost is popped first
         const double u_lo = rb_log(n_lo_chunk), u_hi = rb_log(n_lo_chunk + delta_n);
-        int n_seed = (int)ceil((u_hi - u_lo) / kPanelWidth);
-        if (n_seed < 1)
-            n_seed = 1;
-        if (n_seed > kEngStack - 2)
-            n_seed = kEngStack - 2;
         stk.reset(&ws.outer);
-        for (int k = 0; k < n_seed; k++)
-            stk.push(w, u_lo + (u_hi - u_lo) * k / n_seed, (k + 1 == n_seed) ? u_hi : u_lo + (u_hi - u_lo) * (k + 1) / n_seed, 0);
+        {
+            // segments between the kinks of G(n) that fall inside the chunk (sym_find_kinks)
+            double seg_lo = u_lo;
+#pragma unroll 1
+            for (int g = 0; g <= 4; g++) {
+                double seg_hi = u_hi;
+                if (g < 4) {
+                    const double nk = kink[g];
+                    if (!(nk > n_lo_chunk * (1.0 + 1e-6) && nk < (n_lo_chunk + delta_n) * (1.0 - 1e-6)))
+                        continue;
+                    seg_hi = rb_log(nk);
+                }
+                if (seg_hi > seg_lo) {
+                    int n_seed = (int)ceil((seg_hi - seg_lo) / kPanelWidth);
+                    n_seed = n_seed < 1 ? 1 : (n_seed > 6 ? 6 : n_seed);
+                    for (int k = 0; k < n_seed && stk.room(3); k++)
+                        stk.push(w, seg_lo + (seg_hi - seg_lo) * k / n_seed,
+                                 (k + 1 == n_seed) ? seg_hi : seg_lo + (seg_hi - seg_lo) * (k + 1) / n_seed, 0);
+                    seg_lo = seg_hi;
+                }
+            }
+            if (stk.sp == 0) // degenerate bounds (NaN, infinite): one panel, whose value is NaN
+                stk.push(w, u_lo, u_hi, 0);
+        }
         stk.seal();
 
         PerChan<double> chunk;
