@@ -40,11 +40,11 @@ SEED = 20260
 # predicated-on thread counts of DFMA, DMUL and DADD on the SASS page of one ncu --set full launch
 # of each product kernel, divided by the applications that launch counted
 # (profiles/r01_fast_kernels_details.txt and r01_fast_kernels_summary.md: 4096 seeded pitchy
-# power-law points, 24.7 / 97.4 ms).
-FLOP_PER_APPLICATION = {"symphony": 39.27e3, "heyvaerts": 28.55e3}
+# power-law points, 20.1 / 93.3 ms).
+FLOP_PER_APPLICATION = {"symphony": 39.49e3, "heyvaerts": 28.55e3}
 # DRAM bytes (read + write) per point of the same captures (register spills to local memory; the
 # algorithmic traffic is ~110 B per point): the path does not touch HBM.
-DRAM_BYTES_PER_POINT = {"symphony": (1.06e6 + 47.48e6) / 4096, "heyvaerts": (2.42e6 + 37.82e6) / 4096}
+DRAM_BYTES_PER_POINT = {"symphony": (1.29e6 + 45.68e6) / 4096, "heyvaerts": (2.44e6 + 40.55e6) / 4096}
 
 def parse():
     ap = argparse.ArgumentParser()
