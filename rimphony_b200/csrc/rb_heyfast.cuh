@@ -30,6 +30,7 @@ namespace rb {
 constexpr double kHeyInnerFloor = 1.0;
 constexpr double kHeyInnerWidth = 4.0; // widest NR inner seed panel in t = arccosh(sigma / sigma_min)
 constexpr double kHeyPanelWidth = 2.0; // widest outer panel in the log of the variable
+constexpr double kHeyLightStep = 1e-3; // a step after one that added less than this fraction gets the 7-point rule
 constexpr double kHeyDerivStep = 1e-4; // relative step of the derivative probe
 constexpr int kHeyOuterMaxDepth = 13;  // bisections below a seed after which an outer panel is declared divergent
 
@@ -293,7 +294,7 @@ RB_FN_NOINLINE bool hey_inner_integral(Warp &w, const HeyFastCtx<KIND> &cx, int 
 // rules.  `scale` is the magnitude of the running total, the floor of the acceptance test.
 template <int KIND>
 RB_FN_NOINLINE void hey_outer_integral(Warp &w, const HeyFastCtx<KIND> &cx, int which, int map, double v_lo, double v_hi,
-                                       const PerChan<double> &scale, PerChan<double> &result)
+                                       const PerChan<double> &scale, PerChan<double> &result, bool light = false)
 {
     HeyFastWS &ws = *cx.ws;
     PanelStack stk;
@@ -354,7 +355,9 @@ RB_FN_NOINLINE void hey_outer_integral(Warp &w, const HeyFastCtx<KIND> &cx, int 
         stk.pop(ta, tb, tag);
         const double tc = 0.5 * (ta + tb), thl = 0.5 * (tb - ta);
         warp_fence();
-        const bool narrow = (map == kMapLog || map == kMapNegLog) && (tb - ta) < 0.75;
+        // 7-point rule: narrow panels, and the steps far out whose contribution is already below
+        // 1e-3 of the total (`light`): 1e-3 of that is far inside the tolerance
+        const bool narrow = light || ((map == kMapLog || map == kMapNegLog) && (tb - ta) < 0.75);
         const int n_nodes = narrow ? 7 : 15;
         const double *rx = narrow ? GK7_X : GK15_X;
         const double *rwk = narrow ? GK7_WK : GK15_WK;
@@ -453,7 +456,12 @@ RB_FN_NOINLINE void hey_march(Warp &w, const HeyFastCtx<KIND> &cx, int which, do
 {
     constexpr double kTol = 1e-5, kDeltaScale = 5.0;
     PerChan<bool> keep;
-    RB_FOR_CHAN(c, kEngChan) { keep[c] = false; }
+    PerChan<double> last; // the previous step's contribution
+    RB_FOR_CHAN(c, kEngChan)
+    {
+        keep[c] = false;
+        last[c] = INFINITY;
+    }
     RB_FOR_CHAN(c, 2) { keep[c] = alive[c]; }
 
     for (int steps = 0;; steps++) {
@@ -490,8 +498,11 @@ RB_FN_NOINLINE void hey_march(Warp &w, const HeyFastCtx<KIND> &cx, int which, do
         // the first QR step is integrated in t = sqrt(sigma - sigma_low)
         const int map = (which == kHeyQR && steps == 0) ? kMapSqrt
                                                        : ((lo > 0.0) ? kMapLog : ((hi < 0.0) ? kMapNegLog : kMapLinear));
+        PerChan<bool> minor;
+        RB_FOR_CHAN(c, kEngChan) { minor[c] = !keep[c] || fabs(last[c]) < kHeyLightStep * fabs(val[c]); }
         PerChan<double> contrib;
-        hey_outer_integral<KIND>(w, cx, which, map, lo, hi, val, contrib);
+        hey_outer_integral<KIND>(w, cx, which, map, lo, hi, val, contrib, chan_all(minor, kEngChan));
+        RB_FOR_CHAN(c, 2) { last[c] = contrib[c]; }
 #ifdef RB_TRACE_HEYMARCH
         RB_TRACE_HEYMARCH(which, steps, lo, hi, delta, contrib, val);
 #endif

@@ -33,6 +33,7 @@ namespace rb {
 constexpr double kPeakSpan = 2.6;    // seed half-width in units of n^(-1/3): exp(-(2/3) 2.6^3) = 8e-6, tail beyond < 1e-6
 constexpr double kGrade = 0.875;     // low n: the central panels are cut again at this fraction of the first cut
 constexpr double kUncutSplit = 0.5;  // a side without cuts is seeded as two panels, split at this fraction of the span
+constexpr double kLightChunk = 1e-3; // a chunk after one that added less than this fraction gets the 7-point rule
 constexpr double kInnerFloor = 1.0; // acceptance floor of a gamma panel, fraction of the integral so far
 constexpr double kPanelWidth = 2.302585092994046; // outer panel width in u = ln n (one decade)
 constexpr int kMaxChunks = 400;   // safety net of the chunk loop (the reference has none)
@@ -769,6 +770,15 @@ RB_FN void symphony_point_fast(Warp &w, const Dist &dist, double s, double theta
 
         PerChan<double> chunk;
         RB_FOR_CHAN(c, kEngChan) { chunk[c] = 0.0; }
+        // far up the tail, where the previous chunk added less than kLightChunk of the sum, the
+        // 7-point rule is plenty for a decade of a power law (and 1e-3 of such a chunk is
+        // far inside the tolerance)
+        PerChan<bool> minor;
+        RB_FOR_CHAN(c, kEngChan)
+        {
+            minor[c] = !active[c] || (contrib[c] != 0.0 && fabs(contrib[c]) < kLightChunk * fabs(disc[c] + tail[c]));
+        }
+        const bool light = chunk_no > 0 && chan_all(minor, kEngChan);
         warp_fence();
         tile_clear(w, ws.outer.tile);
         int filled = 0;
@@ -780,7 +790,7 @@ RB_FN void symphony_point_fast(Warp &w, const Dist &dist, double s, double theta
             const double uc = 0.5 * (ua + ub), uhl = 0.5 * (ub - ua);
             warp_fence();
             // outer rule by panel width: K15 for wide panels, K7 for narrow ones
-            const bool narrow = (ub - ua) < kNarrowPanel;
+            const bool narrow = light || (ub - ua) < kNarrowPanel;
             const int n_nodes = narrow ? 7 : 15;
             const double *rx = narrow ? GK7_X : GK15_X;
             const double *rwk = narrow ? GK7_WK : GK15_WK;
