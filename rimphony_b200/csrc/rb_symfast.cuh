@@ -650,12 +650,13 @@ RB_FN void symphony_point_fast(Warp &w, const Dist &dist, double s, double theta
     // integral and parity means truncating it at the same place.  Each chunk is integrated
     // in u = ln n with the outer rule; the derivative probe is a central difference.
     PerChan<double> tail, contrib;
-    PerChan<bool> active;
+    PerChan<bool> active, handed; // handed: left to the faithful continuation by the fidelity guard
     RB_FOR_CHAN(c, kEngChan)
     {
         tail[c] = 0.0;
         contrib[c] = 0.0;
         active[c] = (disc[c] - disc[c] == 0.0); // finite so far
+        handed[c] = false;
     }
     double n_lo_chunk = n_start;
     double delta_n = 1e5, incr_step_factor = 10.0;
@@ -830,14 +831,24 @@ RB_FN void symphony_point_fast(Warp &w, const Dist &dist, double s, double theta
         }
 
         if (n_lo_chunk >= kSensitiveN && s < 1e6) {
+            // Fidelity guard, per accumulator: one whose chunks up here still matter leaves this
+            // path (it is the emission coefficients of hard spectra, as a rule; absorption and
+            // Stokes V decay faster) and is finished by the faithful sequence from the recorded
+            // state; the others carry on here and keep their values.  Without a recorded state
+            // (s < 10) the whole point is handed over.
             PerChan<bool> calm;
             RB_FOR_CHAN(c, kEngChan)
             {
                 calm[c] = !active[c] || !(fabs(chunk[c]) > kSensitiveFraction * fabs(disc[c] + tail[c] + chunk[c]));
+                if (!calm[c]) {
+                    handed[c] = true;
+                    active[c] = false;
+                }
             }
             if (!chan_all(calm, kEngChan)) {
                 w.status |= kStatusRerouted;
-                break;
+                if (!have_snap)
+                    break;
             }
         }
 
@@ -860,6 +871,36 @@ RB_FN void symphony_point_fast(Warp &w, const Dist &dist, double s, double theta
             incr_step_factor = 1.0;
         if (chunk_no == kMaxChunks - 1)
             w.status |= kStatusCapHit;
+    }
+
+    if ((w.status & kStatusRerouted) && have_snap) {
+        // partial handover: the recorded state keeps (tail, contrib) of the accumulators that are
+        // handed over; the others get their final sums and are marked finished, which is how
+        // symphony_tail_faithful treats an accumulator that had converged before the record
+        warp_fence();
+#ifdef RB_DEVICE_BUILD
+        if ((w.lane & 3) == 0)
+#endif
+        {
+            RB_FOR_CHAN(c, kEngChan)
+            {
+                if (!handed[c])
+                    ws.snap[kSnapTail + c] = tail[c];
+            }
+        }
+        unsigned packed = 0;
+#ifdef RB_DEVICE_BUILD
+        const unsigned mask = __ballot_sync(0xffffffffu, handed.v && (w.lane & 3) == 0);
+        for (int c = 0; c < kEngChan; c++)
+            packed |= ((mask >> (4 * c)) & 1u) << c;
+        if (w.lane == 0)
+            ws.snap[kSnapActive] = (double)packed;
+#else
+        for (int c = 0; c < kEngChan; c++)
+            packed |= (handed.v[c] ? 1u : 0u) << c;
+        ws.snap[kSnapActive] = (double)packed;
+#endif
+        warp_fence();
     }
 
     PerChan<double> ans;
