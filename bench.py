@@ -36,15 +36,23 @@ UNIT = "coefficient-sets/s"
 SEED = 20260
 
 # FP64 floating-point operations executed per Gauss-Kronrod application (one pass of the 32 lanes
-# over 31 nodes, or over two 15-node panels in the Symphony gamma integral; FMA = 2): the
-# predicated-on thread counts of DFMA, DMUL and DADD on the SASS page of one ncu --set full launch
-# of each product kernel, divided by the applications that launch counted
-# (profiles/r01_fast_kernels_details.txt and r01_fast_kernels_summary.md: 4096 seeded pitchy
-# power-law points, 20.1 / 93.3 ms).
-FLOP_PER_APPLICATION = {"symphony": 39.49e3, "heyvaerts": 28.55e3}
-# DRAM bytes (read + write) per point of the same captures (register spills to local memory; the
-# algorithmic traffic is ~110 B per point): the path does not touch HBM.
-DRAM_BYTES_PER_POINT = {"symphony": (1.29e6 + 45.68e6) / 4096, "heyvaerts": (2.44e6 + 40.55e6) / 4096}
+# over 31 nodes, or over two 15-node panels in the Symphony gamma integral; FMA = 2) and DRAM bytes
+# per point of the two product kernels.  Not hand-typed: tools/ncu_constants.py derives them from an
+# ncu capture of the head build (the predicated-on thread counts of DFMA / DMUL / DADD and
+# dram__bytes_{read,write}.sum of one launch of each kernel, divided by the rule applications /
+# points that launch counted) and writes profiles/kernel_constants.json, next to the capture.
+CONSTANTS_PATH = os.path.join(ROOT, "profiles", "kernel_constants.json")
+# FP64 flop-equivalents the REFERENCE's algorithm spends per coefficient set on the
+# C2/C3 mix (1.4e6 Symphony integrand evaluations x ~1.3 kflop + 2 x ~3e5 Heyvaerts elements x
+# ~0.3 kflop): sets/s x W_REF is the reference-equivalent work rate, which may exceed the executed
+# rate because the product path shares nodes between coefficients and needs fewer rule applications.
+W_REF_FLOP_PER_SET = 2.0e9
+
+
+def kernel_constants():
+    with open(CONSTANTS_PATH) as f:
+        return json.load(f)
+
 
 def parse():
     ap = argparse.ArgumentParser()
@@ -54,16 +62,71 @@ def parse():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--points", type=int, default=262144,
                     help="points per GPU per step (the full BASELINE configs[2] batch is 10000000)")
-    ap.add_argument("--config", default="pitchy_pl", choices=["pitchy_pl", "powerlaw", "pitchy_kappa"])
+    ap.add_argument("--config", default="pitchy_pl", choices=["pitchy_pl", "powerlaw", "pitchy_kappa", "juettner_sweep"],
+                    help="BASELINE configs: pitchy_pl = C3 (the metric's config), powerlaw = C2, pitchy_kappa = C4, "
+                         "juettner_sweep = C5 (rho_Q, rho_V on the 64 x 128 x 2 grid; --points is ignored)")
+    ap.add_argument("--single-process", action="store_true",
+                    help="north_star's sharding: ONE process drives --gpus devices through "
+                         "rimphony_b200_compute_all_dimensionless_multi on a FIXED batch of --points points "
+                         "(strong scaling, host buffers, host gather inside the timed region)")
+    ap.add_argument("--no-parity", action="store_true", help="skip the (untimed) parity leg")
     ap.add_argument("--cpu-sample", type=int, default=0, help="points of the CPU sample (0 = auto, ~20 s)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     return ap.parse_args()
 
 
+WORKLOADS = {
+    "pitchy_pl": ("BASELINE configs[2] (C3), crank-out-pitchypl shape: pitchy power-law points", 10_000_000),
+    "powerlaw": ("BASELINE configs[1] (C2), benches/powerlaw.rs shape: isotropic power-law points", 1_000_000),
+    "pitchy_kappa": ("BASELINE configs[3] (C4), crank-out-pitchykappa shape incl. s >= 1e5: pitchy kappa points", 10_000_000),
+    "juettner_sweep": ("BASELINE configs[4] (C5), thermal Juettner Faraday sweep: T 64 x s 128 x theta 2 grid", 16384),
+}
+PARITY_FIXTURE = {"pitchy_pl": "pitchy_pl_10k", "powerlaw": "powerlaw_10k", "pitchy_kappa": "pitchy_kappa_10k",
+                  "juettner_sweep": "juettner_sweep"}
+
+
+def coeff_mask_of(config):
+    return 0xC0 if config == "juettner_sweep" else 0xFF
+
+
 def workload_name(config, points):
-    return (f"{config} (crank-out-pitchypl shape: BASELINE configs[2] point distribution, seeded), {points} points per "
-            "GPU per step (a slice of the 10 M-point batch; --points 10000000 runs all of it), all 8 coefficients, "
-            "mode=fast")
+    what, full = WORKLOADS[config]
+    if config == "juettner_sweep":
+        return f"{what} = {full} points per step, rho_Q and rho_V only, mode=fast"
+    part = "the whole batch" if points >= full else f"a seeded slice of the {full}-point batch; --points {full} runs all of it"
+    return f"{what}, {points} points per GPU per step ({part}), all 8 coefficients, mode=fast"
+
+
+def draw(config, n, shard=0):
+    from rimphony_b200.sampler import synthetic_batch
+    kind, s, theta, params = synthetic_batch(config, n, seed=SEED, shard=shard)
+    return kind, s, theta, params
+
+
+def parity_leg(config, device):
+    """Untimed: the product path on the committed golden fixture of this configuration (the fixed
+    1e4-point prefix of the seeded batch; the oracle's outputs are read from the
+    .npz, nothing under oracle/ runs here) -> the `parity` object of the JSON line."""
+    import rimphony_b200 as R
+    from rimphony_b200 import parity as P
+
+    name = PARITY_FIXTURE[config]
+    path = os.path.join(P.GOLDEN_DIR, name + ".npz")
+    if not os.path.exists(path):
+        return {"fixture": name, "error": "fixture missing"}
+    fx = P.load_fixture(name)
+    mask = coeff_mask_of(config)
+    res = R.compute_all_dimensionless_batch(int(fx["kind"]), fx["s"], fx["theta"], list(fx["params"]), device=device,
+                                            coeff_mask=mask)
+    stats = P.parity_stats(res.values, fx["out"], fx.get("lobes"), fx["defined"], mask=mask)
+    out = P.summarize(stats)
+    out["fixture"] = f"tests/golden/{name}.npz"
+    out["bar"] = "rel err <= 1e-3 (Stokes V: of the lobe scale) vs the CPU oracle"
+    out["reference_undefined_note"] = ("entries where the reference's own algorithm moves by > 1e-3 or flips NaN under "
+                                       "epsrel 1e-3 -> 3e-4 or s -> s(1+1e-9) (tests/golden/make_stability.py); excluded "
+                                       "from the other counts" if fx["stability_mask"] else "no stability companion: every entry counted")
+    out["meets_north_star"] = bool(P.meets_north_star(stats))
+    return out
 
 
 class ClockSampler:
@@ -140,56 +203,149 @@ def host_threads():
         return max(1, os.cpu_count() or 1)
 
 
+def cpu_sample(config, first, count):
+    """Points [first, first + count) of the seeded batch of `config` (rank 0's shard; the sampler is
+    prefix-stable, so these are the same points whatever the batch size).  The Juettner sweep is a
+    fixed grid: there the sample strides through it, so that every sample covers the whole (T, s) range."""
+    if config == "juettner_sweep":
+        kind, s, theta, params = draw(config, 0)
+        n = len(s)
+        idx = (np.arange(first, first + count) * 2731) % n  # 2731 is coprime to 16384: a permutation
+        return kind, s[idx], theta[idx], [np.asarray(p)[idx] for p in params]
+    kind, s, theta, params = draw(config, first + count)
+    sl = slice(first, first + count)
+    return kind, s[sl], theta[sl], [np.asarray(p)[sl] if np.ndim(p) else p for p in params]
+
+
 def cpu_baseline(config, n_sample, kind_label):
-    """The oracle (the reference's algorithm; its own bessel.c) on the host cores."""
+    """The oracle (the reference's algorithm; its own bessel.c) on the host cores: a bounded sample
+    of the same seeded batch, in four sub-batches so that the spread is visible."""
     from oracle import oracle as O
-    from rimphony_b200.sampler import synthetic_batch
 
     threads = host_threads()
     if n_sample <= 0:
         n_sample = max(16, 12 * threads)  # ~1 s per point per core => ~15-25 s
-    kind, s, theta, params = synthetic_batch(config, n_sample, seed=SEED)
-    t0 = time.perf_counter()
-    O.batch(kind, s, theta, params, n_threads=threads)
-    dt = time.perf_counter() - t0
-    return {"value": n_sample / dt, "unit": UNIT, "cores": threads, "kind": kind_label,
-            "sample": f"first {n_sample} points of the seeded {config} batch, one point per OpenMP thread, "
-                      f"{dt:.1f} s wall"}, dt
+    parts = 4
+    per = max(1, n_sample // parts)
+    rates = []
+    t_all = 0.0
+    for k in range(parts):
+        kind, s, theta, params = cpu_sample(config, k * per, per)
+        t0 = time.perf_counter()
+        O.batch(kind, s, theta, params, coeff_mask=coeff_mask_of(config), n_threads=threads)
+        dt = time.perf_counter() - t0
+        t_all += dt
+        rates.append(per / dt)
+    return {"value": parts * per / t_all, "unit": UNIT, "cores": threads, "kind": kind_label,
+            "spread": {"min": min(rates), "max": max(rates), "parts": parts},
+            "sample": f"points 0..{parts * per - 1} of the seeded {config} batch in {parts} sub-batches, one point per "
+                      f"OpenMP thread, {t_all:.1f} s wall"}, t_all
 
 
 def run_reference(args):
     """--impl reference: the reference's CPU algorithm.  rimphony itself cannot be built in
     this image (no Rust toolchain, no GSL), so this is the oracle port: the restated
     symphony.rs / heyvaerts.rs control flow driving the reference's own bessel.c compiled
-    in place (oracle/_ref).  Rank 0 alone runs; other ranks exit 0."""
+    in place (oracle/_ref).  Rank 0 alone runs; other ranks exit 0.  Every step computes a
+    DIFFERENT slice of the seeded batch (per-point cost spans more than 10x), so K steps time
+    K x sample distinct points; the per-step spread is reported."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return 0
     from oracle import oracle as O
-    from rimphony_b200.sampler import synthetic_batch
 
     threads = host_threads()
     n_sample = args.cpu_sample if args.cpu_sample > 0 else max(8, 4 * threads)
-    kind, s, theta, params = synthetic_batch(args.config, n_sample, seed=SEED)
-    for _ in range(min(args.warmup, 1)):
-        O.batch(kind, s[: max(threads, 1)], theta[: max(threads, 1)],
-                [np.asarray(p)[: max(threads, 1)] if np.ndim(p) else p for p in params], n_threads=threads)
-    t0 = time.perf_counter()
-    for _ in range(args.steps):
-        O.batch(kind, s, theta, params, n_threads=threads)
-    dt = time.perf_counter() - t0
-    value = args.steps * n_sample / dt
+    mask = coeff_mask_of(args.config)
+    for w in range(min(args.warmup, 1)):
+        kind, s, theta, params = cpu_sample(args.config, 0, max(threads, 1))
+        O.batch(kind, s, theta, params, coeff_mask=mask, n_threads=threads)
+    rates = []
+    t_all = 0.0
+    for k in range(args.steps):
+        kind, s, theta, params = cpu_sample(args.config, k * n_sample, n_sample)
+        t0 = time.perf_counter()
+        O.batch(kind, s, theta, params, coeff_mask=mask, n_threads=threads)
+        dt = time.perf_counter() - t0
+        t_all += dt
+        rates.append(n_sample / dt)
+    value = args.steps * n_sample / t_all
+    spread = {"min": min(rates), "median": float(np.median(rates)), "max": max(rates), "steps": args.steps}
+    points = WORKLOADS[args.config][1] if args.config == "juettner_sweep" else args.points
     line = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
-        "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True, "scaling": "weak",
+        "warmup": args.warmup, "ms_per_step": 1e3 * t_all / args.steps, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": workload_name(args.config, args.points),
-                   "note": "CPU reference arm: each step is a bounded sample of the workload"},
-        "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": "port",
-                         "sample": f"{n_sample} points per step x {args.steps} steps of the seeded {args.config} batch"},
+        "config": {"workload": workload_name(args.config, points),
+                   "note": "CPU reference arm: each step is a bounded, distinct sample of the workload"},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": "port", "spread": spread,
+                         "sample": f"{n_sample} points per step x {args.steps} steps = points 0..{args.steps * n_sample - 1} "
+                                   f"of the seeded {args.config} batch (a different slice every step)"},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
+    print(json.dumps(line))
+    return 0
+
+
+def run_single_process(args):
+    """north_star's own sharding, measured: ONE process, a FIXED batch of --points points in host
+    memory, rimphony_b200_compute_all_dimensionless_multi cutting it into contiguous slices for
+    --gpus devices (one host thread + stream each), results gathered by the host.  Strong scaling;
+    the timed region holds H2D, kernels, D2H and the gather; wall clock around synchronous calls."""
+    import torch
+
+    import rimphony_b200 as R
+
+    n_dev = args.gpus
+    if R.device_count() < n_dev:
+        raise SystemExit(f"--single-process --gpus {n_dev}: only {R.device_count()} devices visible")
+    n = WORKLOADS[args.config][1] if args.config == "juettner_sweep" else args.points
+    mask = coeff_mask_of(args.config)
+    kind, s, theta, params = draw(args.config, n)
+    h_s = torch.from_numpy(s).pin_memory().numpy()
+    h_theta = torch.from_numpy(theta).pin_memory().numpy()
+    h_params = [torch.from_numpy(np.ascontiguousarray(p)).pin_memory().numpy() if np.ndim(p) else p for p in params]
+    flush = [torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=f"cuda:{d}") for d in range(n_dev)]
+
+    def step():
+        for f in flush:
+            f.fill_(1)
+        return R.compute_all_dimensionless_batch(kind, h_s, h_theta, h_params, coeff_mask=mask, n_devices=n_dev)
+
+    for _ in range(args.warmup):
+        step()
+    for d in range(n_dev):
+        torch.cuda.synchronize(d)
+    launches0 = R.kernel_launch_count()
+    sampler = ClockSampler(0)
+    sampler.start()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        out = step()
+    for d in range(n_dev):
+        torch.cuda.synchronize(d)
+    dt = time.perf_counter() - t0
+    clocks = sampler.stop()
+    launches = R.kernel_launch_count() - launches0
+    value = n * args.steps / dt
+    h2d = 8 * n * (2 + sum(1 for p in params if np.ndim(p))) + 8 * n_dev * sum(1 for p in params if not np.ndim(p))
+    d2h = 8 * 8 * n + 4 * n
+    line = {
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": n_dev, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+        "dtype": "f64", "data": "synthetic",
+        "config": {"workload": workload_name(args.config, n) + f"; FIXED batch of {n} points sharded over {n_dev} GPUs",
+                   "seed": SEED, "l2": "flushed between steps (256 MB write per device)",
+                   "nan_rate": float(np.isnan(out.values).any(axis=0).mean()),
+                   "sharding": f"single process, rimphony_b200_compute_all_dimensionless_multi: {n_dev} contiguous slices, "
+                               "one host thread + stream per device, host gather, no collective",
+                   "timing": "host wall clock around synchronous C-ABI calls (copies and gather inside)"},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
+        "gpu_launches": int(launches), "clocks": clocks,
+    }
+    if not args.no_parity:
+        line["parity"] = parity_leg(args.config, 0)
     print(json.dumps(line))
     return 0
 
@@ -198,12 +354,13 @@ def main():
     args = parse()
     if args.impl == "reference":
         return run_reference(args)
+    if args.single_process:
+        return run_single_process(args)
 
     import torch
     import torch.distributed as dist
 
     import rimphony_b200 as R
-    from rimphony_b200.sampler import synthetic_batch
 
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -221,9 +378,9 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
-    n = args.points
-    kind, s, theta, params = synthetic_batch(args.config, n, seed=SEED, shard=rank)
-    n_params = len(params)
+    mask = coeff_mask_of(args.config)
+    n = WORKLOADS[args.config][1] if args.config == "juettner_sweep" else args.points
+    kind, s, theta, params = draw(args.config, n, shard=rank)
 
     # --- device-resident leg -------------------------------------------------
     d_s = torch.from_numpy(s).to(dev)
@@ -240,7 +397,7 @@ def main():
         with torch.cuda.stream(stream):
             flush.fill_(1)
             R.compute_all_dimensionless_device(kind, d_s, d_theta, d_params, d_out, d_status, stream=stream,
-                                               synchronize=False)
+                                               coeff_mask=mask, synchronize=False)
 
     torch.cuda.synchronize()
     for _ in range(args.warmup):
@@ -261,11 +418,12 @@ def main():
     ms_dev = e0.elapsed_time(e1)
 
     # per-kernel device time and work counters of one more (untimed) step, for the roofline
-    res = R.compute_all_dimensionless_batch(kind, s, theta, params, device=local_rank, extras=True)
+    res = R.compute_all_dimensionless_batch(kind, s, theta, params, device=local_rank, coeff_mask=mask, extras=True)
     k_ms = res.kernel_ms
     apps_sym = float(res.counters[0].astype(np.float64).sum())
     apps_hey = float(res.counters[1].astype(np.float64).sum())
-    nan_rate = float(np.isnan(res.values).any(axis=0).mean())
+    nan_rate = float(np.isnan(res.values[[c for c in range(8) if (mask >> c) & 1]]).any(axis=0).mean())
+    rerouted = float(((res.status & 8) != 0).mean())
 
     # --- end-to-end leg: host buffers through the public C ABI --------------
     h_s = torch.from_numpy(s).pin_memory().numpy()
@@ -274,7 +432,7 @@ def main():
 
     def step_host():
         flush.fill_(1)
-        return R.compute_all_dimensionless_batch(kind, h_s, h_theta, h_params, device=local_rank)
+        return R.compute_all_dimensionless_batch(kind, h_s, h_theta, h_params, device=local_rank, coeff_mask=mask)
 
     step_host()
     barrier()
@@ -294,32 +452,46 @@ def main():
         e2e_value = whole_job_value(n, world, args.steps, ms_e2e)
         peak = R.fp64_peak_tflops(local_rank)
         # The two product kernels run concurrently on two streams and share the SMs, so the roofline
-        # is taken over both: FP64 flops executed by the step's Symphony + Heyvaerts launches (rule
-        # applications counted by the kernels x flops per application from ncu) over the CUDA-event
-        # span of the step; `dominant` names the larger contributor.
-        flops_sym = apps_sym * FLOP_PER_APPLICATION["symphony"]
-        flops_hey = apps_hey * FLOP_PER_APPLICATION["heyvaerts"]
+        # is taken over both: FP64 flops executed by one step's Symphony + Heyvaerts launches (rule
+        # applications counted by the kernels x flops per application from the ncu capture) over the
+        # CUDA-event time of a step of the TIMED region (recorded on the launching stream; it also
+        # holds the normalisation, the classification and the L2 flush, which makes the figure a
+        # lower bound); `dominant` names the larger contributor.
+        kc = kernel_constants()
+        flops_sym = apps_sym * kc["flop_per_application"]["symphony"]
+        flops_hey = apps_hey * kc["flop_per_application"]["heyvaerts"]
         dominant = "heyvaerts" if flops_hey >= flops_sym else "symphony"
-        achieved = (flops_sym + flops_hey) / (k_ms[3] * 1e-3) * 1e-12
+        step_s = ms_dev / args.steps * 1e-3
+        achieved = (flops_sym + flops_hey) / step_s * 1e-12
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms_dev / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f64", "data": "synthetic",
             "config": {"workload": workload_name(args.config, n), "seed": SEED, "l2": "flushed between steps (256 MB write)",
-                       "nan_rate": nan_rate, "sharding": f"{world} independent shards, no data-path collective"},
+                       "nan_rate": nan_rate, "rerouted_rate": rerouted,
+                       "sharding": f"{world} independent shards, no data-path collective"},
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
             "gpu_launches": int(launches),
             "clocks": clocks,
             "roofline": {"bound": "fp64", "kernel": "k_symphony_fast + k_heyvaerts_fast (concurrent; larger share: " + dominant + ")",
                          "achieved": achieved, "peak": peak, "unit": "TFLOP/s",
                          "frac": achieved / peak if peak else None,
-                         "traffic": (DRAM_BYTES_PER_POINT["symphony"] + DRAM_BYTES_PER_POINT["heyvaerts"]) * n,
-                         "traffic_note": "bytes per launch, scaled per point from the ncu --set full capture in profiles/",
+                         "traffic": (kc["dram_bytes_per_point"]["symphony"] + kc["dram_bytes_per_point"]["heyvaerts"]) * n,
+                         "traffic_note": "bytes per launch, scaled per point from the ncu --set full capture in profiles/ "
+                                         "(local-memory spills; the algorithmic traffic is ~110 B per point)",
+                         "constants": {"source": kc.get("source"), "flop_per_application": kc["flop_per_application"]},
                          "peak_source": "measured in this run: register-resident DFMA kernel "
                                         "(MEASURED_PEAKS.json has no FP64 figure)",
-                         "kernel_ms": {"normalize": k_ms[0], "symphony": k_ms[1], "heyvaerts": k_ms[2], "span": k_ms[3]},
-                         "gk31_applications_per_point": {"symphony": apps_sym / n, "heyvaerts": apps_hey / n}},
+                         "kernel_ms": {"normalize": k_ms[0], "symphony": k_ms[1], "heyvaerts": k_ms[2], "span": k_ms[3],
+                                       "note": "one extra untimed step, the library's own CUDA events"},
+                         "gk31_applications_per_point": {"symphony": apps_sym / n, "heyvaerts": apps_hey / n},
+                         "reference_equivalent_tflops": value * W_REF_FLOP_PER_SET * 1e-12,
+                         "reference_equivalent_note": "sets/s x W_ref (2.0e9 flop-equivalents per set, SURVEY 8d): the rate at "
+                                                      "which the reference's own work is retired; exceeds `achieved` because the "
+                                                      "product path shares nodes and needs fewer rule applications"},
         }
+        if not args.no_parity:
+            line["parity"] = parity_leg(args.config, local_rank)
         if not args.no_cpu_baseline and world == 1:
             cb, _ = cpu_baseline(args.config, args.cpu_sample, "port")
             line["cpu_baseline"] = cb

@@ -32,7 +32,7 @@
 extern "C" {
 #endif
 
-#define RIMPHONY_B200_ABI_VERSION 1
+#define RIMPHONY_B200_ABI_VERSION 2
 
 /* Distribution kinds and the order of their parameter columns.
  *   POWER_LAW         p [, gamma_min, gamma_max, gamma_cutoff]        1 or 4 columns
@@ -93,13 +93,18 @@ enum rimphony_b200_mode {
 #define RIMPHONY_B200_STATUS_REROUTED 8u    /* FAST mode handed the point to the FAITHFUL sequence: its reference
                                                value is set by where the reference's quadrature loses the J_n^2
                                                peak (n > 1e10, hard spectra), see DESIGN.md */
+#define RIMPHONY_B200_STATUS_REFERENCE_DIVERGES 16u /* FAST mode, rho_Q / rho_V of a power law with gamma_min = 1 at
+                                               s < 0.38 (rho_V) / 0.35 (rho_Q): the reference's adaptive quadrature
+                                               cannot converge on the |sigma - s|^(2s-1) singularity of the
+                                               quasi-resonant integrand and returns NaN (heyvaerts.rs:175-177); so
+                                               does this path, without integrating */
 
 typedef struct rimphony_b200_options {
     uint32_t struct_size;          /* sizeof(rimphony_b200_options); 0-initialise the rest for defaults */
     int32_t mode;                  /* enum rimphony_b200_mode */
     uint32_t coeff_mask;           /* bit i: compute output slot i; 0 means all eight */
     uint32_t param_broadcast_mask; /* bit j: params[j] points to ONE value used for every point */
-    int32_t device;                /* CUDA ordinal; -1 = the calling thread's current device */
+    int32_t device_plus_one;       /* CUDA ordinal + 1; 0 = the calling thread's current device */
     int32_t reserved0;
     double epsrel_gamma;           /* Symphony gamma integral, 0 = reference value 1e-3 (symphony.rs:376) */
     double epsrel_n;               /* Symphony n integral,     0 = 1e-3 (symphony.rs:266) */
@@ -135,19 +140,29 @@ int rimphony_b200_compute_all_dimensionless_ex(int kind, int64_t n_points, const
                                                const rimphony_b200_extras *extras);
 
 /* Same, but every array pointer (s, theta, params[j], out8, status, extras->*) is a
- * DEVICE pointer on opts->device and `stream` is a cudaStream_t passed as void*
+ * DEVICE pointer on the selected device and `stream` is a cudaStream_t passed as void*
  * (NULL = the library's own stream for that device).  Nothing is copied; the
  * call returns after the kernels have been enqueued and, if `synchronize` is
- * nonzero, completed. */
+ * nonzero, completed.  Output slots that coeff_mask does not request are left
+ * untouched (the host entry points fill them with NaN).
+ *
+ * Asynchronous use (synchronize = 0): the library keeps one set of scratch buffers per
+ * device, so batched calls on one device are serialised ON THE DEVICE: a call enqueued
+ * while an earlier one is still running (on the same or on another stream) first waits
+ * for that call's completion event.  The host never blocks for this, results are ordered
+ * after `stream` as usual, and rimphony_b200_last_kernel_ms() is meaningful only after a
+ * synchronize = 1 call. */
 int rimphony_b200_compute_all_dimensionless_device(int kind, int64_t n_points, const double *s, const double *theta,
                                                    const double *const *params, int n_params,
                                                    const rimphony_b200_options *opts, double *out8,
                                                    int32_t *status, const rimphony_b200_extras *extras,
                                                    void *stream, int synchronize);
 
-/* Shard the batch evenly over `n_devices` GPUs of this box (0 = all visible):
- * one host thread and stream per device, contiguous slices, no inter-GPU
- * communication; the host gathers by construction (disjoint output slices). */
+/* Shard the batch evenly over the first `n_devices` GPUs of this box (0 = all visible;
+ * opts->device_plus_one is ignored): one host thread and stream per device, contiguous
+ * slices, no inter-GPU communication.  Each shard's eight result rows are copied straight
+ * into their slices of the caller's [8][n_points] array, so the host gathers by
+ * construction.  Host arrays. */
 int rimphony_b200_compute_all_dimensionless_multi(int kind, int64_t n_points, const double *s, const double *theta,
                                                   const double *const *params, int n_params,
                                                   const rimphony_b200_options *opts, double *out8,

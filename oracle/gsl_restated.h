@@ -49,6 +49,7 @@ typedef struct {
     /* statistics for SURVEY/BASELINE style probes */
     size_t max_size_seen;
     unsigned long n_rule_applications;
+    int trace; /* debug: print every bisection (parity studies) */
 } orc_workspace;
 
 static const double orc_xgk31[16] = {
@@ -107,6 +108,7 @@ static inline void orc_workspace_init(orc_workspace *w, size_t limit)
     w->size = 0;
     w->max_size_seen = 0;
     w->n_rule_applications = 0;
+    w->trace = 0;
 }
 
 static inline double orc_rescale_error(double err, double result_abs, double result_asc)
@@ -208,6 +210,10 @@ static inline size_t orc_ws_argmax(const orc_workspace *w)
     return best;
 }
 
+/* Debug aid for the parity studies (tests/golden/make_stability.py and friends): when set, every
+ * bisection of a QAG call whose workspace has `trace` on is printed to stderr. */
+#include <stdio.h>
+
 /* gsl_integration_qag with key = GSL_INTEG_GAUSS31. */
 static inline int orc_qag31(orc_fn f, void *ctx, double a, double b,
                             double epsabs, double epsrel, orc_workspace *w,
@@ -294,6 +300,9 @@ static inline int orc_qag31(orc_fn f, void *ctx, double a, double b,
         }
 
         tolerance = ORC_GSL_MAX(epsabs, epsrel * fabs(area));
+        if (w->trace)
+            fprintf(stderr, "  qag it %zu bisect [%.15g, %.15g] r_old %.6g e_old %.3g -> r (%.6g, %.6g) e (%.3g, %.3g) | area %.8g errsum %.3g tol %.3g\n",
+                    iteration, a_i, b_i, r_i, e_i, area1, area2, error1, error2, area, errsum, tolerance);
 
         if (errsum > tolerance) {
             if (roundoff_type1 >= 6 || roundoff_type2 >= 20)

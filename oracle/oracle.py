@@ -55,6 +55,20 @@ class Stats(ctypes.Structure):
         ("n_heyvaerts_jy", ctypes.c_uint64),
         ("hey_nr_val", ctypes.c_double),
         ("hey_qr_val", ctypes.c_double),
+        ("hey_fail_stage", ctypes.c_int),
+        ("hey_fail_outer_status", ctypes.c_int),
+        ("hey_fail_inner_status", ctypes.c_int),
+        ("hey_fail_inner_kind", ctypes.c_int),
+        ("hey_fail_lo", ctypes.c_double),
+        ("hey_fail_hi", ctypes.c_double),
+        ("hey_fail_inner_var", ctypes.c_double),
+        ("hey_nan_kind", ctypes.c_int),   # 0 none, 1 NR, 2 QR
+        ("hey_nan_sigma", ctypes.c_double),
+        ("hey_nan_pomega", ctypes.c_double),
+        ("hey_nan_x", ctypes.c_double),
+        ("hey_nan_gamma", ctypes.c_double),
+        ("hey_nan_mu", ctypes.c_double),
+        ("hey_nan_value", ctypes.c_double),
     ]
 
 
@@ -100,6 +114,8 @@ def lib():
         ctypes.c_uint, _c_double_p, _c_double_p, i32]
     L.orc_batch_compute_all_dimensionless.restype = i32
     L.orc_num_threads.restype = i32
+    L.orc_set_epsrel.argtypes = [dbl, dbl]
+    L.orc_set_epsrel.restype = None
     for name in ("orc_ref_bessel_j", "orc_ref_bessel_dj", "orc_test_bessel_i"):
         getattr(L, name).argtypes = [dbl, dbl]
         getattr(L, name).restype = dbl
@@ -173,6 +189,12 @@ def batch(kind, s, theta, params, coeff_mask=0xFF, n_threads=0):
         kind, n, s.ctypes.data_as(_c_double_p), theta.ctypes.data_as(_c_double_p), ptrs, len(cols),
         coeff_mask, out.ctypes.data_as(_c_double_p), lobes.ctypes.data_as(_c_double_p), n_threads)
     return out, lobes
+
+
+def set_epsrel(symphony=0.0, heyvaerts=0.0):
+    """Stability studies only (tests/golden/make_stability.py): the epsrel of the oracle's QAG calls;
+    0 restores the reference's 1e-3."""
+    lib().orc_set_epsrel(symphony, heyvaerts)
 
 
 def num_threads():

@@ -50,6 +50,23 @@ extern double pkgw_bessel_dj(double n, double x);
 
 #define ORC_MAXV(a, b) ((a) > (b) ? (a) : (b))
 
+/* The reference passes epsrel = 1e-3 to every QAG call of this path (src/gsl.rs:169-180 through
+ * symphony.rs:327,251 and heyvaerts.rs:98,225,278).  These two are that constant.  They can be
+ * changed ONLY for the stability study of tests/golden/make_stability.py, which asks how far the
+ * reference's own output moves when its own tolerance is tightened (where it moves by more than
+ * 1e-3 the reference value is not defined to 1e-3).  Set before a batch, never during one. */
+static double g_sym_epsrel = 1e-3;
+static double g_hey_epsrel = 1e-3;
+
+static int g_trace_hey_outer = 0;
+void orc_set_trace(int heyvaerts_outer) { g_trace_hey_outer = heyvaerts_outer; }
+
+void orc_set_epsrel(double symphony_epsrel, double heyvaerts_epsrel)
+{
+    g_sym_epsrel = symphony_epsrel > 0. ? symphony_epsrel : 1e-3;
+    g_hey_epsrel = heyvaerts_epsrel > 0. ? heyvaerts_epsrel : 1e-3;
+}
+
 /* ------------------------------------------------------------------------- */
 /* Distribution functions                                                     */
 
@@ -367,7 +384,7 @@ static double sym_gamma_integral(double n, void *ctx)
     }
 
     st->cur_n = n;
-    status = orc_qag31(sym_gamma_integrand, st, gamma0, gamma1, 0., 1e-3, st->gamma_ws, &contrib,
+    status = orc_qag31(sym_gamma_integrand, st, gamma0, gamma1, 0., g_sym_epsrel, st->gamma_ws, &contrib,
                        &abserr);
     if (st->stats) {
         st->stats->n_gamma_qag++;
@@ -409,7 +426,7 @@ static int sym_n_integration(sym_state *st, double n_start, double *out)
         if (delta_n < n_start / incr_step_factor)
             delta_n *= incr_step_factor;
 
-        status = orc_qag31(sym_gamma_integral, st, n_start, n_start + delta_n, 0., 1e-3, n_ws,
+        status = orc_qag31(sym_gamma_integral, st, n_start, n_start + delta_n, 0., g_sym_epsrel, n_ws,
                            &contrib, &abserr);
         if (st->stats) {
             st->stats->n_chunks++;
@@ -630,6 +647,7 @@ typedef struct {
     double outer_var; /* closure variable of the inner integrands */
     orc_workspace *iws;
     orc_stats *stats;
+    int stage; /* diagnostics: which part of orc_heyvaerts is running */
 } hey_state;
 
 /* src/heyvaerts.rs:194-201 */
@@ -769,13 +787,30 @@ static double hey_f_nr_element(hey_state *st)
     return -2. * ORC_PI * INVERSE_C * z * st->pomega * hey_dfdsigma(st);
 }
 
+static void hey_note_nonfinite(hey_state *st, int kind, double v)
+{
+    if (st->stats && !isfinite(v) && st->stats->hey_nan_kind == 0) {
+        st->stats->hey_nan_kind = 1 + kind;
+        st->stats->hey_nan_sigma = st->sigma;
+        st->stats->hey_nan_pomega = st->pomega;
+        st->stats->hey_nan_x = st->x;
+        st->stats->hey_nan_gamma = st->gamma;
+        st->stats->hey_nan_mu = st->mu;
+        st->stats->hey_nan_value = v;
+    }
+}
+
 static double hey_nr_inner(double sigma, void *ctx)
 {
     hey_state *st = (hey_state *)ctx;
     if (st->stats)
         st->stats->n_heyvaerts_element++;
     hey_fill_coord_vars(st, sigma, st->outer_var);
-    return st->stokes == ORC_STOKES_Q ? hey_h_nr_element(st) : hey_f_nr_element(st);
+    {
+        const double v = st->stokes == ORC_STOKES_Q ? hey_h_nr_element(st) : hey_f_nr_element(st);
+        hey_note_nonfinite(st, 0, v);
+        return v;
+    }
 }
 
 static double hey_qr_inner(double pomega, void *ctx)
@@ -784,7 +819,11 @@ static double hey_qr_inner(double pomega, void *ctx)
     if (st->stats)
         st->stats->n_heyvaerts_element++;
     hey_fill_coord_vars(st, st->outer_var, pomega);
-    return st->stokes == ORC_STOKES_Q ? hey_h_qr_element(st) : hey_f_qr_element(st);
+    {
+        const double v = st->stokes == ORC_STOKES_Q ? hey_h_qr_element(st) : hey_f_qr_element(st);
+        hey_note_nonfinite(st, 1, v);
+        return v;
+    }
 }
 
 /* src/heyvaerts.rs:213-250 */
@@ -800,9 +839,15 @@ static double hey_nr_outer_integrand(double pomega, void *ctx)
         return 0.;
 
     st->outer_var = pomega;
-    status = orc_qag31(hey_nr_inner, st, sigma_min, sigma_max, 0., 1e-3, st->iws, &result, &abserr);
-    if (st->stats)
+    status = orc_qag31(hey_nr_inner, st, sigma_min, sigma_max, 0., g_hey_epsrel, st->iws, &result, &abserr);
+    if (st->stats) {
         st->stats->n_heyvaerts_qag++;
+        if (status != ORC_SUCCESS && !st->stats->hey_fail_inner_status) {
+            st->stats->hey_fail_inner_status = status;
+            st->stats->hey_fail_inner_kind = 0;
+            st->stats->hey_fail_inner_var = pomega;
+        }
+    }
     return status == ORC_SUCCESS ? result : NAN;
 }
 
@@ -818,18 +863,31 @@ static double hey_qr_outer_integrand(double sigma, void *ctx)
     int status;
 
     st->outer_var = sigma;
-    status = orc_qag31(hey_qr_inner, st, -pomega_max, pomega_max, 0., 1e-3, st->iws, &result, &abserr);
-    if (st->stats)
+    status = orc_qag31(hey_qr_inner, st, -pomega_max, pomega_max, 0., g_hey_epsrel, st->iws, &result, &abserr);
+    if (st->stats) {
         st->stats->n_heyvaerts_qag++;
+        if (status != ORC_SUCCESS && !st->stats->hey_fail_inner_status) {
+            st->stats->hey_fail_inner_status = status;
+            st->stats->hey_fail_inner_kind = 1;
+            st->stats->hey_fail_inner_var = sigma;
+        }
+    }
     return status == ORC_SUCCESS ? result : NAN;
 }
 
 static double hey_outer_integral(hey_state *st, orc_workspace *ows, orc_fn f, double a, double b)
 {
     double result, abserr;
-    int status = orc_qag31(f, st, a, b, 0., 1e-3, ows, &result, &abserr);
-    if (st->stats)
+    int status = orc_qag31(f, st, a, b, 0., g_hey_epsrel, ows, &result, &abserr);
+    if (st->stats) {
         st->stats->n_heyvaerts_qag++;
+        if (status != ORC_SUCCESS && !st->stats->hey_fail_outer_status) {
+            st->stats->hey_fail_outer_status = status;
+            st->stats->hey_fail_stage = st->stage;
+            st->stats->hey_fail_lo = a;
+            st->stats->hey_fail_hi = b;
+        }
+    }
     return status == ORC_SUCCESS ? result : NAN;
 }
 
@@ -858,6 +916,7 @@ double orc_heyvaerts(const orc_dist *d, int stokes, double s, double theta, orc_
     iws = (orc_workspace *)malloc(sizeof(orc_workspace));
     orc_workspace_init(ows, 4096);
     orc_workspace_init(iws, 4096);
+    ows->trace = g_trace_hey_outer;
     st.iws = iws;
 
     pomega_left = -3. * st.sigma0;
@@ -865,10 +924,12 @@ double orc_heyvaerts(const orc_dist *d, int stokes, double s, double theta, orc_
     delta_left = pomega_right;
     delta_right = pomega_right;
 
+    st.stage = 1;
     nr_val = hey_outer_integral(&st, ows, hey_nr_outer_integrand, pomega_left, pomega_right);
     if (isnan(nr_val))
         goto done;
 
+    st.stage = 2;
     while (keep_going) {
         double contrib;
 
@@ -892,6 +953,7 @@ double orc_heyvaerts(const orc_dist *d, int stokes, double s, double theta, orc_
     }
 
     keep_going = 1;
+    st.stage = 3;
 
     while (keep_going) {
         double contrib, rel_deriv, err;
@@ -914,6 +976,7 @@ double orc_heyvaerts(const orc_dist *d, int stokes, double s, double theta, orc_
     sigma_low = ORC_MAXV(st.sigma0, INVERSE_SQRT_3 * pow(st.sigma0, 1.5));
     delta_sigma = st.sigma0;
     keep_going = 1;
+    st.stage = 4;
 
     while (keep_going) {
         double contrib;
@@ -951,6 +1014,32 @@ done:
     free(ows);
     free(iws);
     return result;
+}
+
+/* Parity-study hook: the outer integrands of orc_heyvaerts at one value of the outer variable
+ * (which = 0: NR at pomega, 1: QR at sigma); NaN when the inner QAG fails, as in the flow above. */
+double orc_test_hey_outer_integrand(const orc_dist *d, int stokes, double s, double theta, int which,
+                                    double outer_var, orc_stats *stats)
+{
+    hey_state st;
+    orc_workspace *iws = (orc_workspace *)malloc(sizeof(orc_workspace));
+    double v;
+    memset(&st, 0, sizeof(st));
+    st.d = d;
+    st.stokes = stokes;
+    st.s = s;
+    st.cos_observer_angle = cos(theta);
+    st.sin_observer_angle = sin(theta);
+    st.sigma0 = s * sin(theta);
+    st.sigma0_sq = st.sigma0 * st.sigma0;
+    st.stats = stats;
+    orc_workspace_init(iws, 4096);
+    st.iws = iws;
+    v = which ? hey_qr_outer_integrand(outer_var, &st) : hey_nr_outer_integrand(outer_var, &st);
+    if (stats)
+        stats->max_gamma_intervals = iws->max_size_seen; /* reused: live intervals of the inner QAG */
+    free(iws);
+    return v;
 }
 
 /* ------------------------------------------------------------------------- */

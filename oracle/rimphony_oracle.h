@@ -33,6 +33,14 @@ typedef struct {
     uint64_t n_heyvaerts_qag;
     uint64_t n_heyvaerts_jy;
     double hey_nr_val, hey_qr_val;
+    /* where a Heyvaerts calculation failed (diagnostics for the parity study; 0 = it did not):
+     * stage 1 NR centre, 2 NR right march, 3 NR left march, 4 QR march; the outer QAG's status;
+     * the status, outer variable and kind (0 NR, 1 QR) of the FIRST inner QAG that failed */
+    int hey_fail_stage, hey_fail_outer_status, hey_fail_inner_status, hey_fail_inner_kind;
+    double hey_fail_lo, hey_fail_hi, hey_fail_inner_var;
+    /* the first non-finite element value: kind (0 none, 1 NR, 2 QR), its coordinates and value */
+    int hey_nan_kind;
+    double hey_nan_sigma, hey_nan_pomega, hey_nan_x, hey_nan_gamma, hey_nan_mu, hey_nan_value;
 } orc_stats;
 
 int orc_dist_init(orc_dist *d, int kind, const double *params, int n_params);
@@ -57,7 +65,13 @@ int orc_batch_compute_all_dimensionless(int kind, int64_t n_points, const double
                                         int n_params, unsigned coeff_mask, double *out8,
                                         double *lobes4, int n_threads);
 int orc_num_threads(void);
+/* stability studies only (tests/golden/make_stability.py); 0 restores the reference's 1e-3 */
+void orc_set_epsrel(double symphony_epsrel, double heyvaerts_epsrel);
+/* debug: print the bisections of the Heyvaerts outer QAG calls to stderr */
+void orc_set_trace(int heyvaerts_outer);
 
+double orc_test_hey_outer_integrand(const orc_dist *d, int stokes, double s, double theta, int which,
+                                    double outer_var, orc_stats *stats);
 double orc_ref_bessel_j(double n, double x);
 double orc_ref_bessel_dj(double n, double x);
 double orc_test_bessel_i(double nu, double x);

@@ -42,7 +42,7 @@ POWER_LAW, THERMAL_JUETTNER, PITCHY_PL, PITCHY_KAPPA = 0, 1, 2, 3
 
 MODE_FAST, MODE_FAITHFUL, MODE_FUSED_ALL, MODE_FUSED = 0, 1, 2, 3
 
-STATUS_NAN, STATUS_CAP_HIT, STATUS_NORM_FAILED, STATUS_REROUTED = 1, 2, 4, 8
+STATUS_NAN, STATUS_CAP_HIT, STATUS_NORM_FAILED, STATUS_REROUTED, STATUS_REFERENCE_DIVERGES = 1, 2, 4, 8, 16
 DIAG_GAMMA_INTEGRAND, DIAG_GAMMA_INTEGRAL, DIAG_N_INTEGRAL, DIAG_GAMMA_CONTRIBUTION = 0, 1, 2, 3
 
 COEFFICIENT_NAMES = ("j_I", "alpha_I", "j_Q", "alpha_Q", "j_V", "alpha_V", "rho_Q", "rho_V")
@@ -86,7 +86,7 @@ def make_options(mode=MODE_FAST, coeff_mask=0xFF, broadcast_mask=0, device=-1, e
     o.mode = int(mode)
     o.coeff_mask = int(coeff_mask)
     o.param_broadcast_mask = int(broadcast_mask)
-    o.device = int(device)
+    o.device_plus_one = int(device) + 1 if int(device) >= 0 else 0
     o.epsrel_gamma = float(epsrel_gamma)
     o.epsrel_n = float(epsrel_n)
     o.epsrel_heyvaerts_inner = float(epsrel_heyvaerts_inner)

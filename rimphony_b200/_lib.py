@@ -22,7 +22,7 @@ class Options(ctypes.Structure):
         ("mode", ctypes.c_int32),
         ("coeff_mask", ctypes.c_uint32),
         ("param_broadcast_mask", ctypes.c_uint32),
-        ("device", ctypes.c_int32),
+        ("device_plus_one", ctypes.c_int32),
         ("reserved0", ctypes.c_int32),
         ("epsrel_gamma", ctypes.c_double),
         ("epsrel_n", ctypes.c_double),

@@ -75,6 +75,7 @@ constexpr unsigned kStatusNaN = 1u;        // at least one coefficient is NaN
 constexpr unsigned kStatusCapHit = 2u;     // an interval list filled up
 constexpr unsigned kStatusNormFailed = 4u; // normalisation integral failed
 constexpr unsigned kStatusRerouted = 8u;   // computed with the reference's exact rule sequence (fidelity guard)
+constexpr unsigned kStatusRefDiverges = 16u; // rho: NaN because the reference's quadrature fails here (rb_heyfast.cuh)
 
 // ---------------------------------------------------------------------------
 // Gauss-Kronrod (15, 31) tables laid out by lane: lane l < 31 holds the node

@@ -79,9 +79,13 @@ RB_FN double log_pitch_term(double k, double sin2)
     return (k == 0.0) ? 0.0 : 0.5 * k * rb_log(sin2);
 }
 
-// calc_f and calc_f_derivatives in one go.
+// calc_f and calc_f_derivatives in one go.  `sin2_exact`: sin^2(xi) when the caller knows it
+// without the cancellation of 1 - cos^2 (the Heyvaerts product path, where |cos xi| -> 1 at the
+// ends of the inner range and the rounded 1 - cos^2 turns into 0 or a negative number); NaN =
+// compute it from cos_xi as the reference does.
 template <int KIND>
-RB_FN void dist_eval(const Dist &d, double gamma, double cos_xi, double &f, double &dfdg, double &dfdcx)
+RB_FN void dist_eval(const Dist &d, double gamma, double cos_xi, double &f, double &dfdg, double &dfdcx,
+                     double sin2_exact = NAN)
 {
     if (KIND == kDistPowerLaw) {
         if (gamma < d.gamma_min || gamma > d.gamma_max) {
@@ -102,14 +106,14 @@ RB_FN void dist_eval(const Dist &d, double gamma, double cos_xi, double &f, doub
             f = dfdg = dfdcx = 0.0;
             return;
         }
-        const double sin2 = 1.0 - cos_xi * cos_xi;
+        const double sin2 = (sin2_exact == sin2_exact) ? sin2_exact : 1.0 - cos_xi * cos_xi;
         const double g2m1 = gamma * gamma - 1.0;
         f = d.norm * rb_exp(log_pitch_term(d.k, sin2) - d.p * rb_log(gamma) - gamma * d.inv_gamma_cutoff) /
             (gamma * sqrt(g2m1));
         dfdg = -f * ((d.p + 1.0) / gamma + gamma / g2m1 + d.inv_gamma_cutoff);
         dfdcx = -f * d.k * cos_xi / sin2;
     } else {
-        const double sin2 = 1.0 - cos_xi * cos_xi;
+        const double sin2 = (sin2_exact == sin2_exact) ? sin2_exact : 1.0 - cos_xi * cos_xi;
         f = d.norm * rb_exp(log_pitch_term(d.k, sin2) -
                          (d.kappa + 1.0) * rb_log(1.0 + (gamma - 1.0) * d.inv_kappa_width) -
                          gamma * d.inv_gamma_cutoff);

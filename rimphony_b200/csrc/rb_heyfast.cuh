@@ -34,6 +34,34 @@ constexpr double kHeyLightStep = 1e-3; // a step after one that added less than 
 constexpr double kHeyDerivStep = 1e-4; // relative step of the derivative probe
 constexpr int kHeyOuterMaxDepth = 13;  // bisections below a seed after which an outer panel is declared divergent
 
+// Where the reference's own quadrature gives up.  A distribution with 1/(gamma^2 beta) in it (the
+// power laws with gamma_min = 1) makes df/dsigma diverge like (gamma - 1)^-3/2 where gamma -> 1.  In
+// the QR domain that is the single point sigma = s, pomega = s cos(theta) (the line gamma = 1 touches
+// the edge x = 0 of the domain there; for s > 3 the point lies outside pomega_max).  The QR
+// elements vanish at that point (pi^2 x^2 J'Y' - pi^2 pomega^2 JY + t3 -> 0), the next order is
+// J_sigma(x)^2 ~ x^(2 sigma): along sigma = s the inner integrand goes like delta^(s - 3/2) in the
+// distance delta to the end of the pomega range and the outer integrand like |sigma - s|^(2 s - 1),
+// an integrable singularity for s < 1/2 (a cusp above).  The reference's QAG (epsrel 1e-3, no
+// extrapolation) bisects towards sigma = s; the inner integrals next to it chase their own
+// end-point singularity down to the last ulps of the pomega range, where the rounded cos(xi)
+// reaches 1 and sin^k(xi), 1 / sin^2(xi) turn into NaN (heyvaerts.rs:194-201, pitchy_pl.rs:44-61):
+// QAG error -> NaN coefficient (heyvaerts.rs:175-177).  Whether the outer QAG converges before it
+// samples such a sigma is decided by the exponent: measured on 14 096 oracle points
+// (tests/golden/heyvaerts_low_s.md) the reference returns NaN for 97 % of the points with
+// s < 0.3 and a finite value for 97 % of those with s > 0.5 (rho_Q; rho_V the same 0.04 higher),
+// and the set moves with the reference's tolerance (1e-4: +15 % NaN, 1e-5: +40 %) while its
+// finite values do not.  The product path integrates the same integrand with cos(xi) -> +-1
+// handled exactly (HeyNode::fill), so it would return the finite value of the integral there;
+// to stay a drop-in it reports what the reference reports: NaN + STATUS_REFERENCE_DIVERGES below
+// these thresholds, without spending the 10-50 k rule applications such a point costs.
+// A point that has used this many rule applications is not going to converge (the ones that do
+// need 0.5-10 k): it is chasing the x^(k-2) end-point behaviour of d f / d cos(xi) at small k or
+// theta -> 0, where the reference fails as well (tests/golden/heyvaerts_low_s.md).  NaN + CAP_HIT,
+// and the tail of the persistent kernel stays short.
+constexpr unsigned kHeyAppBudget = 20000;
+constexpr double kHeyRefDivergesQ = 0.35; // rho_Q: s below which the reference's quadrature fails
+constexpr double kHeyRefDivergesV = 0.38; // rho_V
+
 struct HeyFastWS {
     EngLevel inner, outer;
 };
@@ -70,6 +98,7 @@ RB_FN_NOINLINE bool hey_inner_integral(Warp &w, const HeyFastCtx<KIND> &cx, int 
     const HeyGeometry &g = cx.g;
     PanelStack stk;
     stk.reset(&ws.inner);
+    lockstep_tick(); // a seeding tick
 
     bool empty = false;
     // QR with pomega_max = sqrt(sigma^2 - sigma0^2): x -> 0 at both ends of the pomega range and the
@@ -181,6 +210,7 @@ RB_FN_NOINLINE bool hey_inner_integral(Warp &w, const HeyFastCtx<KIND> &cx, int 
         stk.pop(ta, tb, tag);
         const double tc = 0.5 * (ta + tb), thl = 0.5 * (tb - ta);
         warp_fence();
+        lockstep_tick(); // a rule-application tick
 #ifdef RB_DEVICE_BUILD
         {
             double vals[2];
@@ -350,6 +380,11 @@ RB_FN_NOINLINE void hey_outer_integral(Warp &w, const HeyFastCtx<KIND> &cx, int 
     int filled = 0;
 
     while (stk.sp > 0) {
+        if (w.n_apply_lanes > kHeyAppBudget) {
+            RB_FOR_CHAN(c, 2) { result[c] = NAN; }
+            w.status |= kStatusCapHit;
+            return;
+        }
         double ta, tb;
         int tag;
         stk.pop(ta, tb, tag);
@@ -552,6 +587,16 @@ RB_FN void heyvaerts_point_fast(Warp &w, const Dist &dist, double s, double thet
         qr_val[c] = 0.0;
     }
     RB_FOR_CHAN(c, 2) { alive[c] = true; }
+    if ((KIND == kDistPowerLaw || KIND == kDistPitchyPL) && dist.gamma_min == 1.0 && s < kHeyRefDivergesV) {
+        // the reference's NaN region (see kHeyRefDivergesQ)
+        w.status |= kStatusRefDiverges;
+        RB_FOR_CHAN(c, 2) { alive[c] = (c == 0) && !(s < kHeyRefDivergesQ); }
+        if (s < kHeyRefDivergesQ) {
+            out2[0] = NAN;
+            out2[1] = NAN;
+            return;
+        }
+    }
 
     // The QR part first (heyvaerts.rs:156-185; the two parts are independent sums): where the
     // calculation fails it is almost always here (the QR domain of a point with s <= 3 touches

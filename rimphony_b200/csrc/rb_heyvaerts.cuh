@@ -48,10 +48,30 @@ struct HeyNode {
         x = (x_exact == x_exact) ? x_exact : sqrt(sigma * sigma - pomega * pomega - g.sigma0_sq);
         const double t = g.sigma0 * g.sin_th;
         const double gamma = (sigma - pomega * g.cos_th) / t;
-        const double mu = (sigma * g.cos_th - pomega) / (t * sqrt(gamma * gamma - 1.0));
+        double mu = (sigma * g.cos_th - pomega) / (t * sqrt(gamma * gamma - 1.0));
+
+        // sin^2(xi) = 1 - mu^2 = x^2 sin^2(theta) / ((sigma - pomega cos(theta))^2 - t^2) identically.
+        // Where the caller knows x without cancellation (the product path's substitutions) this
+        // form is used: at the ends of the inner range, where mu -> +-1, the rounded mu reaches
+        // exactly 1 (or beyond) a few 1e-6 of the range before the end, and the pitch-angle factor
+        // sin^k(xi), d f / d cos(xi) ~ 1 / sin^2(xi) turn into 0/0 there.
+        double sin2 = NAN;
+#ifndef RB_NO_EXACT_SIN2
+        if (x_exact == x_exact) {
+            const double q = sigma - pomega * g.cos_th;
+            const double xs = x * g.sin_th;
+            sin2 = xs * xs / ((q - t) * (q + t));
+            if (sin2 <= 1.0) {
+                const double mag = sqrt(1.0 - sin2);
+                if (fabs(mu) > mag || !(mu == mu))
+                    mu = (sigma * g.cos_th - pomega < 0.0) ? -mag : mag;
+            } else
+                sin2 = NAN;
+        }
+#endif
 
         double f, dfdg, dfdcxi;
-        dist_eval<KIND>(d, gamma, mu, f, dfdg, dfdcxi);
+        dist_eval<KIND>(d, gamma, mu, f, dfdg, dfdcxi, sin2);
         const double g_term = dfdg / t;
         double mu_term = 0.0;
         if (dfdcxi != 0.0) {

@@ -137,10 +137,25 @@ __global__ void __launch_bounds__(kThreadsPerBlock, 4) k_symphony_diag(BatchArgs
 #ifndef RB_FAST_BLOCKS
 #define RB_FAST_BLOCKS 5 // resident CTAs per SM the product kernels are compiled for (96 registers; +5 % over 4)
 #endif
+#ifndef RB_FAST_WARPS
+#define RB_FAST_WARPS 4 // warps per CTA of the product kernels
+#endif
+constexpr int kFastWarps = RB_FAST_WARPS;
+constexpr int kFastThreads = kFastWarps * 32;
+static_assert(RB_LOCKSTEP != 2 || kFastWarps % 4 == 0, "per-scheduler lock-step groups need a multiple of four warps");
+
+// After its last point a warp keeps the lock-step barrier company until its whole group is idle.
+__device__ __forceinline__ void lockstep_drain()
+{
+#if RB_LOCKSTEP
+    while (lockstep_tick(true) != lockstep_group_threads()) {
+    }
+#endif
+}
 
 // The product path: compact engine (rb_engine.cuh, rb_symfast.cuh).
 template <int KIND>
-__global__ void __launch_bounds__(kThreadsPerBlock, RB_FAST_BLOCKS) k_symphony_fast(BatchArgs a)
+__global__ void __launch_bounds__(kFastThreads, RB_FAST_BLOCKS) k_symphony_fast(BatchArgs a)
 {
     extern __shared__ double smem[];
     const int warp = threadIdx.x >> 5;
@@ -203,6 +218,7 @@ __global__ void __launch_bounds__(kThreadsPerBlock, RB_FAST_BLOCKS) k_symphony_f
                 atomicOr(&a.status[i], (int)st);
         }
     }
+    lockstep_drain();
 }
 
 template <int KIND, bool FUSED>
@@ -255,7 +271,7 @@ __global__ void __launch_bounds__(kThreadsPerBlock, 4) k_heyvaerts(BatchArgs a)
 
 // The product path for rho_Q, rho_V: compact engine (rb_engine.cuh, rb_heyfast.cuh).
 template <int KIND>
-__global__ void __launch_bounds__(kThreadsPerBlock, RB_FAST_BLOCKS) k_heyvaerts_fast(BatchArgs a)
+__global__ void __launch_bounds__(kFastThreads, RB_FAST_BLOCKS) k_heyvaerts_fast(BatchArgs a)
 {
     extern __shared__ double smem[];
     const int warp = threadIdx.x >> 5;
@@ -295,6 +311,7 @@ __global__ void __launch_bounds__(kThreadsPerBlock, RB_FAST_BLOCKS) k_heyvaerts_
                 atomicOr(&a.status[i], (int)st);
         }
     }
+    lockstep_drain();
 }
 
 template <int KIND>
@@ -370,10 +387,10 @@ template <int KIND>
 int stage_symphony_fast(const BatchArgs &a, int sm_count, cudaStream_t st)
 {
     int grid = 0;
-    const size_t smem = kWarpsPerBlock * sizeof(SymFastWS);
-    if (set_smem(k_symphony_fast<KIND>, smem) || persistent_grid(k_symphony_fast<KIND>, smem, sm_count, &grid))
+    const size_t smem = kFastWarps * sizeof(SymFastWS);
+    if (set_smem(k_symphony_fast<KIND>, smem) || persistent_grid(k_symphony_fast<KIND>, smem, sm_count, &grid, kFastThreads))
         return 1;
-    k_symphony_fast<KIND><<<grid, kThreadsPerBlock, smem, st>>>(a);
+    k_symphony_fast<KIND><<<grid, kFastThreads, smem, st>>>(a);
     g_launches++;
     RB_CUDA(cudaGetLastError());
     return 0;
@@ -403,10 +420,10 @@ template <int KIND>
 int stage_heyvaerts_fast(const BatchArgs &a, int sm_count, cudaStream_t st)
 {
     int grid = 0;
-    const size_t smem = kWarpsPerBlock * sizeof(HeyFastWS);
-    if (set_smem(k_heyvaerts_fast<KIND>, smem) || persistent_grid(k_heyvaerts_fast<KIND>, smem, sm_count, &grid))
+    const size_t smem = kFastWarps * sizeof(HeyFastWS);
+    if (set_smem(k_heyvaerts_fast<KIND>, smem) || persistent_grid(k_heyvaerts_fast<KIND>, smem, sm_count, &grid, kFastThreads))
         return 1;
-    k_heyvaerts_fast<KIND><<<grid, kThreadsPerBlock, smem, st>>>(a);
+    k_heyvaerts_fast<KIND><<<grid, kFastThreads, smem, st>>>(a);
     g_launches++;
     RB_CUDA(cudaGetLastError());
     return 0;

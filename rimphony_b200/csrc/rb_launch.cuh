@@ -61,6 +61,7 @@ struct BatchArgs {
     // order[class][t - (points in the classes before)].  The per-point cost spans 10x and a
     // warp works on one point at a time, so handing out the long points first is what keeps the
     // tail of the persistent kernel short.
+    double hey_free_below;            // scheduling hint: Heyvaerts points with s below this cost nothing (0 = none)
     int *order;                       // [2 kernels][kCostClasses][n]
     unsigned long long *class_counts; // [2 kernels][kCostClasses]
 };
@@ -134,10 +135,10 @@ int set_smem(K kernel, size_t bytes)
 }
 
 template <class K>
-int persistent_grid(K kernel, size_t smem, int sm_count, int *grid)
+int persistent_grid(K kernel, size_t smem, int sm_count, int *grid, int threads = kThreadsPerBlock)
 {
     int per_sm = 0;
-    RB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, kThreadsPerBlock, smem));
+    RB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, threads, smem));
     if (per_sm < 1)
         return ::rbhost::fail("kernel does not fit on an SM (smem %zu)", smem);
     *grid = per_sm * sm_count; // every resident CTA slot, a multiple of the SM count

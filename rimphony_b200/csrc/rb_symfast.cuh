@@ -228,6 +228,7 @@ RB_FN_NOINLINE void sym_gamma_integral(Warp &w, const SymFastCtx<KIND> &cx, doub
         }
     }
 
+    lockstep_tick(); // a seeding tick
     warp_fence();
 #ifdef RB_DEVICE_BUILD
     if (w.lane < 2) // orders n and n + 1 side by side
@@ -428,6 +429,7 @@ RB_FN_NOINLINE void sym_gamma_integral(Warp &w, const SymFastCtx<KIND> &cx, doub
             tb0 = mid;
         }
         warp_fence(); // the previous reduce has finished reading the tile
+        lockstep_tick(); // a rule-application tick
 
 #ifdef RB_DEVICE_BUILD
         {
@@ -735,6 +737,9 @@ RB_FN void symphony_point_fast(Warp &w, const Dist &dist, double s, double theta
         {
             grow_c[c] = !active[c] || deriv[c] == 0.0 || (contrib[c] != 0.0 && fabs(deriv[c] / contrib[c]) < kDerivTol);
         }
+#ifdef RB_TRACE_VOTE
+        RB_TRACE_VOTE(chunk_no, n_lo_chunk, delta_n, active, grow_c);
+#endif
         if (chan_all(grow_c, kEngChan))
             delta_n *= incr_step_factor;
         if (delta_n < n_lo_chunk / incr_step_factor)

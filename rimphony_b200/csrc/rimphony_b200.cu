@@ -50,8 +50,10 @@ __global__ void __launch_bounds__(256) k_dfma_peak(double *sink, int iters, doub
 }
 
 // Cost classes of the product kernels (rb_launch.cuh BatchArgs::order).  Symphony: rule
-// applications grow with s (500 at s < 1 to 3000 at s ~ 1e4).  Heyvaerts: s sin(theta) < 0.5
-// costs 5-13 k applications with the J/Y elements, < 3 about 3 k, the rest 1.3 k.
+// applications grow with s (500 at s < 1 to 3000 at s ~ 1e4).  Heyvaerts: 0.38 <= s < 1 costs
+// 3.7-5.3 k applications (the quasi-resonant integrand is singular at sigma = s), s sin(theta) < 3
+// about 2.3 k, the rest 0.5 k; the power-law points below s = 0.38 cost nothing (the reference's
+// NaN region, rb_heyfast.cuh) and go last.
 __global__ void k_classify(rbhost::BatchArgs a)
 {
     const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
@@ -60,7 +62,9 @@ __global__ void k_classify(rbhost::BatchArgs a)
     const double s = a.s[i];
     const double sigma0 = s * sin(a.theta[i]);
     const int cs = (s >= 300.0) ? 0 : ((s >= 10.0) ? 1 : 2);
-    const int ch = (sigma0 < 0.5) ? 0 : ((sigma0 < 3.0) ? 1 : 2); // NaN lands in the last class
+    int ch = (s < 1.0) ? 0 : ((sigma0 < 3.0) ? 1 : 2); // NaN lands in the last class
+    if (a.hey_free_below > 0.0 && s < a.hey_free_below)
+        ch = 2;
     const unsigned long long ks = atomicAdd(&a.class_counts[cs], 1ULL);
     a.order[(size_t)cs * a.n + ks] = (int)i;
     const unsigned long long kh = atomicAdd(&a.class_counts[rbhost::kCostClasses + ch], 1ULL);
@@ -139,6 +143,15 @@ struct DeviceBuffer {
     }
 };
 
+// Restores the calling thread's current CUDA device on scope exit: the entry points select the
+// device they run on and must not leave that as a side effect (callers such as torch keep their
+// own notion of the current device).
+struct DeviceGuard {
+    int saved = -1;
+    DeviceGuard() { if (cudaGetDevice(&saved) != cudaSuccess) saved = -1; }
+    ~DeviceGuard() { if (saved >= 0) cudaSetDevice(saved); }
+};
+
 struct DeviceContext {
     bool ready = false;
     int device = -1;
@@ -146,6 +159,8 @@ struct DeviceContext {
     cudaStream_t stream = nullptr;       // Symphony + copies
     cudaStream_t stream_hey = nullptr;   // Heyvaerts, overlaps the Symphony tail
     cudaEvent_t ev[8] = {};
+    cudaEvent_t ev_done = nullptr;       // completion of the most recent batched call on this device
+    bool have_done = false;
     DeviceBuffer in, out, scratch, counters, reroute, handover, order;
     float last_ms[4] = {0, 0, 0, 0};
     std::mutex lock;
@@ -176,6 +191,7 @@ int get_context(int device, DeviceContext **out)
         RB_CUDA(cudaStreamCreateWithFlags(&c.stream_hey, cudaStreamNonBlocking));
         for (auto &e : c.ev)
             RB_CUDA(cudaEventCreate(&e));
+        RB_CUDA(cudaEventCreateWithFlags(&c.ev_done, cudaEventDisableTiming));
         c.device = device;
         c.ready = true;
     }
@@ -203,7 +219,9 @@ ResolvedOptions resolve(const rimphony_b200_options *o)
     r.mode = tmp.mode;
     r.coeff_mask = tmp.coeff_mask ? (tmp.coeff_mask & 0xFFu) : 0xFFu;
     r.bcast = tmp.param_broadcast_mask;
-    r.device = tmp.device;
+    // ordinal + 1, so that a zero-initialised (or older, shorter) struct means "the calling
+    // thread's current device"
+    r.device = (tmp.device_plus_one > 0) ? tmp.device_plus_one - 1 : -1;
     if (tmp.epsrel_gamma > 0)
         r.eps_gamma = tmp.epsrel_gamma;
     if (tmp.epsrel_n > 0)
@@ -244,6 +262,7 @@ int launch_kind(DeviceContext &c, BatchArgs a, const ResolvedOptions &o, cudaStr
 
     RB_CUDA(cudaMemsetAsync(counters, 0, 4 * sizeof(unsigned long long), st));
     RB_CUDA(cudaEventRecord(c.ev[0], st));
+    a.hey_free_below = (KIND == kDistPowerLaw || KIND == kDistPitchyPL) ? kHeyRefDivergesQ : 0.0;
 
     // 1. normalisation (+ the cost-ordered schedule of the product kernels)
     if (stage_normalize<KIND>(a, c.sm_count, st))
@@ -395,10 +414,18 @@ int run_device(int kind, int64_t n, const double *s, const double *theta, const 
 
     cudaStream_t user = static_cast<cudaStream_t>(stream);
     cudaStream_t st = user ? user : c.stream;
+    // The work counters, the reroute list, the hand-over records and the cost-ordered schedule
+    // are per-device scratch: a call enqueued while an earlier asynchronous one (possibly on
+    // another stream) is still running must not touch them.  It waits, on the device, for that
+    // call's completion event; the host does not block.
+    if (c.have_done)
+        RB_CUDA(cudaStreamWaitEvent(st, c.ev_done, 0));
     if (status)
         RB_CUDA(cudaMemsetAsync(status, 0, (size_t)n * sizeof(int32_t), st));
     if (launch(c, kind, a, o, user))
         return 1;
+    RB_CUDA(cudaEventRecord(c.ev_done, st));
+    c.have_done = true;
     if (synchronize) {
         RB_CUDA(cudaStreamSynchronize(st));
         if (collect_times(c))
@@ -407,10 +434,13 @@ int run_device(int kind, int64_t n, const double *s, const double *theta, const 
     return 0;
 }
 
+// `out_stride`: distance in doubles between two slots of the caller's out8 (n for a whole batch;
+// the batch size of the caller when this call computes one shard of it, see _multi).
 int run_host(int kind, int64_t n, const double *s, const double *theta, const double *const *params, int n_params,
              const rimphony_b200_options *opts, double *out8, int32_t *status, const rimphony_b200_extras *extras,
-             int device_override)
+             int device_override, int64_t out_stride = 0)
 {
+    DeviceGuard restore_device;
     if (n < 0)
         return fail("n_points is negative");
     if (check_params(kind, n_params))
@@ -494,7 +524,11 @@ int run_host(int kind, int64_t n, const double *s, const double *theta, const do
     if (run_device(kind, n, d_s, d_theta, d_params, n_params, o, d_out8, d_status, &dev_extras, nullptr, 0, c))
         return 1;
 
-    RB_CUDA(cudaMemcpyAsync(out8, d_out8, 8 * (size_t)n * sizeof(double), cudaMemcpyDeviceToHost, c.stream));
+    if (out_stride > n) // a shard: each slot row lands in its slice of the caller's [8][out_stride] array
+        RB_CUDA(cudaMemcpy2DAsync(out8, (size_t)out_stride * sizeof(double), d_out8, (size_t)n * sizeof(double),
+                                  (size_t)n * sizeof(double), 8, cudaMemcpyDeviceToHost, c.stream));
+    else
+        RB_CUDA(cudaMemcpyAsync(out8, d_out8, 8 * (size_t)n * sizeof(double), cudaMemcpyDeviceToHost, c.stream));
     if (status)
         RB_CUDA(cudaMemcpyAsync(status, d_status, (size_t)n * sizeof(int32_t), cudaMemcpyDeviceToHost, c.stream));
     if (want_lobes)
@@ -546,6 +580,7 @@ int rimphony_b200_compute_all_dimensionless_device(int kind, int64_t n_points, c
     ResolvedOptions o = resolve(opts);
     if (o.mode < 0 || o.mode > 3)
         return fail("unknown mode %d", o.mode);
+    DeviceGuard restore_device;
     DeviceContext *cp = nullptr;
     if (get_context(o.device, &cp))
         return 1;
@@ -562,40 +597,61 @@ int rimphony_b200_compute_all_dimensionless_multi(int kind, int64_t n_points, co
         return fail("n_points is negative");
     if (check_params(kind, n_params))
         return 1;
+    if (n_points == 0)
+        return 0;
+    if (!s || !theta || !params || !out8)
+        return fail("null array pointer");
+    for (int j = 0; j < n_params; j++)
+        if (!params[j])
+            return fail("params[%d] is null", j);
+    const ResolvedOptions o = resolve(opts);
+    if (o.mode < 0 || o.mode > 3)
+        return fail("unknown mode %d", o.mode);
     int visible = 0;
     RB_CUDA(cudaGetDeviceCount(&visible));
     if (visible < 1)
         return fail("no CUDA device visible");
+    if (visible > kMaxDevices)
+        visible = kMaxDevices;
     if (n_devices <= 0 || n_devices > visible)
         n_devices = visible;
-    if (n_points == 0)
-        return 0;
-    const ResolvedOptions o = resolve(opts);
+    if ((int64_t)n_devices > n_points)
+        n_devices = (int)n_points;
 
-    // Contiguous slices; out8 is slot-major over the WHOLE batch, so each shard
-    // computes into a private [8][m] block that is scattered afterwards.
+    // Contiguous slices, devices 0 .. n_devices-1 (opts->device_plus_one does not apply here).  out8
+    // is slot-major over the WHOLE batch: every shard copies its eight rows straight into their
+    // slices of it (one strided device-to-host copy), the host gathers by construction.
     std::vector<std::thread> workers;
     std::vector<int> rc(n_devices, 0);
     std::vector<std::string> msg(n_devices);
-    for (int d = 0; d < n_devices; d++) {
-        const int64_t lo = n_points * d / n_devices, hi = n_points * (d + 1) / n_devices;
-        workers.emplace_back([&, d, lo, hi]() {
-            const int64_t m = hi - lo;
-            if (m == 0)
-                return;
-            std::vector<const double *> cols(n_params);
-            for (int j = 0; j < n_params; j++)
-                cols[j] = ((o.bcast >> j) & 1u) ? params[j] : params[j] + lo;
-            std::vector<double> block(8 * (size_t)m);
-            rc[d] = run_host(kind, m, s + lo, theta + lo, cols.data(), n_params, opts, block.data(),
-                             status ? status + lo : nullptr, nullptr, d);
-            if (rc[d]) {
-                msg[d] = g_error;
-                return;
-            }
-            for (int c = 0; c < 8; c++)
-                memcpy(out8 + (size_t)c * n_points + lo, block.data() + (size_t)c * m, (size_t)m * sizeof(double));
-        });
+    try {
+        for (int d = 0; d < n_devices; d++) {
+            const int64_t lo = n_points * d / n_devices, hi = n_points * (d + 1) / n_devices;
+            workers.emplace_back([&, d, lo, hi]() {
+                try {
+                    const int64_t m = hi - lo;
+                    if (m == 0)
+                        return;
+                    const double *cols[kMaxParams] = {};
+                    for (int j = 0; j < n_params; j++)
+                        cols[j] = ((o.bcast >> j) & 1u) ? params[j] : params[j] + lo;
+                    rc[d] = run_host(kind, m, s + lo, theta + lo, cols, n_params, opts, out8 + lo,
+                                     status ? status + lo : nullptr, nullptr, d, n_points);
+                    if (rc[d])
+                        msg[d] = g_error; // thread-local: carry it to the caller's thread
+                } catch (const std::exception &e) {
+                    rc[d] = 1;
+                    msg[d] = e.what();
+                } catch (...) {
+                    rc[d] = 1;
+                    msg[d] = "unknown exception";
+                }
+            });
+        }
+    } catch (const std::exception &e) { // thread creation failed: join what was started
+        for (auto &t : workers)
+            t.join();
+        return fail("could not start the per-device worker threads: %s", e.what());
     }
     for (auto &t : workers)
         t.join();
@@ -623,7 +679,7 @@ int rimphony_b200_compute_dimensionless(int kind, const double *params, int n_pa
     memset(&o, 0, sizeof o);
     o.struct_size = sizeof o;
     o.coeff_mask = 1u << slot;
-    o.device = -1;
+    o.device_plus_one = 0; // the current device
     const double *cols[kMaxParams];
     for (int j = 0; j < n_params; j++)
         cols[j] = params + j;
@@ -800,6 +856,7 @@ int rimphony_b200_last_kernel_ms(int device, float out_ms[4])
 {
     if (!out_ms)
         return fail("null pointer");
+    DeviceGuard restore_device;
     DeviceContext *cp = nullptr;
     if (get_context(device, &cp))
         return 1;
@@ -811,6 +868,7 @@ int rimphony_b200_fp64_peak_tflops(int device, double *out_tflops)
 {
     if (!out_tflops)
         return fail("null pointer");
+    DeviceGuard restore_device;
     DeviceContext *cp = nullptr;
     if (get_context(device, &cp))
         return 1;
@@ -869,6 +927,8 @@ void rimphony_b200_shutdown(void)
         c.order.release();
         for (auto &e : c.ev)
             cudaEventDestroy(e);
+        cudaEventDestroy(c.ev_done);
+        c.have_done = false;
         cudaStreamDestroy(c.stream);
         cudaStreamDestroy(c.stream_hey);
         c.ready = false;

@@ -50,19 +50,25 @@ CONFIGS = {
 }
 
 
-def synthetic_batch(config, n, seed=20260, shard=0):
+def synthetic_batch(config, n, seed=20260, shard=0, sequential=False):
     """Draw ``n`` points of a named configuration.
 
     Returns ``(kind, s, theta, params)`` where ``params`` is the list of columns of
     the C ABI (sampled columns as arrays, fixed trailing columns as scalars).
-    ``shard`` selects an independent Philox key, e.g. the rank of a GPU.
+    ``shard`` selects an independent Philox key, e.g. the rank of a GPU.  Every column
+    has its own counter block of that key, so the first m points of a batch do not depend
+    on n: the 10^4-point parity fixtures are prefixes of the benchmark batches.
+    ``sequential=True`` is the round-1 draw (one stream, column after column), kept so that
+    tests/golden/make_golden.py still regenerates the round-1 fixtures.
     """
     if config == "juettner_sweep":
         return juettner_sweep()
     kind, cols, fixed = CONFIGS[config]
     rng = np.random.Generator(np.random.Philox(key=[int(seed), int(shard)]))
     drawn = {}
-    for name, is_log, lo, hi in cols:
+    for j, (name, is_log, lo, hi) in enumerate(cols):
+        if not sequential:
+            rng = np.random.Generator(np.random.Philox(key=[int(seed), int(shard)], counter=[0, 0, 0, j + 1]))
         drawn[name] = Sampler(is_log, lo, hi, rng).get(n)
     s = drawn.pop("s")
     theta = drawn.pop("theta")

@@ -36,6 +36,12 @@ FIXTURES = {
     # from the 400-point fixture through the shard argument)
     "pitchy_pl_4k": ("pitchy_pl", 4096),
     "pitchy_kappa_2k": ("pitchy_kappa", 2048),
+    # the fixed 1e4-point prefix of each benchmark batch (rank 0's shard of bench.py:
+    # seed SEED, shard 0, column-wise counter blocks so that a prefix does not depend on the
+    # batch size).  bench.py reads these for the `parity` object of its JSON line.
+    "pitchy_pl_10k": ("pitchy_pl", 10000),
+    "powerlaw_10k": ("powerlaw", 10000),
+    "pitchy_kappa_10k": ("pitchy_kappa", 10000),
 }
 
 
@@ -64,13 +70,33 @@ def run(name):
         kind = O.PITCHY_PL
         s, theta = 10 ** rng.uniform(6, 7, n), rng.uniform(0.05, 1.5, n)
         params = [rng.uniform(1.8, 4.0, n), rng.uniform(0.0, 3.0, n), 1.0, 1e12, 1e10]
+    elif name == "demo_powerlaw":
+        # examples/demo-powerlaw.rs:80-98, the 64-step "almostuniform1" sweep
+        from rimphony_b200.crank_out import GAMMA_CUTOFF, GAMMA_MAX, GAMMA_MIN, demo_almostuniform1
+        cols = demo_almostuniform1()
+        kind, s, theta = O.POWER_LAW, cols["s"], cols["theta"]
+        params = [cols["p"], GAMMA_MIN, GAMMA_MAX, GAMMA_CUTOFF]
+    elif name == "crank_pitchypl_64":
+        # the 64 points `crank_out --seed 1 --count 64 pitchypl 1 100 0.3 1.5 2 3 0 2` draws
+        import argparse
+        from rimphony_b200.crank_out import GAMMA_CUTOFF, GAMMA_MAX, GAMMA_MIN, samplers
+        args = argparse.Namespace(tool="pitchypl", S_MIN=1.0, S_MAX=100.0, THETA_MIN=0.3, THETA_MAX=1.5, P_MIN=2.0, P_MAX=3.0,
+                                  K_MIN=0.0, K_MAX=2.0)
+        _, samp = samplers(args, np.random.default_rng(1))
+        cols = {nm: np.atleast_1d(sm.get(64)) for nm, sm in samp}
+        kind, s, theta = O.PITCHY_PL, cols["s"], cols["theta"]
+        params = [cols["p"], cols["k"], GAMMA_MIN, GAMMA_MAX, GAMMA_CUTOFF]
     elif name == "juettner_sweep":
         kind, s, theta, params = synthetic_batch("juettner_sweep", 0)
         sel = np.arange(0, len(s), 37)  # 443 of the 16384 grid points
         s, theta, params = s[sel], theta[sel], [params[0][sel]]
     else:
         config, n = FIXTURES[name]
-        kind, s, theta, params = synthetic_batch(config, n, seed=SEED, shard=(7 if name.endswith("k") else 0))
+        if name.endswith("_10k"):
+            kind, s, theta, params = synthetic_batch(config, n, seed=SEED, shard=0)
+        else:  # round-1 fixtures: the sequential draw
+            kind, s, theta, params = synthetic_batch(config, n, seed=SEED, shard=(7 if name.endswith("k") else 0),
+                                                     sequential=True)
     n = len(s)
     mask = 0xC0 if name == "juettner_sweep" else 0xFF
     out, lobes = O.batch(kind, s, theta, params, coeff_mask=mask)

@@ -33,7 +33,7 @@ def test_library_exports_every_declared_symbol():
     for name in names:
         assert hasattr(L, name), f"{name} is declared in the header but not exported"
     assert sorted(_lib.EXPORTED_SYMBOLS) == names
-    assert L.rimphony_b200_abi_version() == 1
+    assert L.rimphony_b200_abi_version() == 2
 
 
 def test_header_is_plain_c_and_struct_layout_matches(tmp_path):
@@ -44,7 +44,7 @@ def test_header_is_plain_c_and_struct_layout_matches(tmp_path):
 #include "rimphony_b200.h"
 int main(void) {
     printf("%zu %zu %zu %zu %zu %zu\n", sizeof(rimphony_b200_options), offsetof(rimphony_b200_options, coeff_mask),
-           offsetof(rimphony_b200_options, device), offsetof(rimphony_b200_options, epsrel_gamma),
+           offsetof(rimphony_b200_options, device_plus_one), offsetof(rimphony_b200_options, epsrel_gamma),
            offsetof(rimphony_b200_options, epsrel_heyvaerts_outer), sizeof(rimphony_b200_extras));
     return 0;
 }''')
@@ -52,7 +52,7 @@ int main(void) {
     subprocess.check_call([GCC, "-std=c99", "-Wall", "-Werror", "-pedantic", "-I", os.path.join(ROOT, "include"), str(src), "-o", str(exe)])
     got = [int(v) for v in subprocess.check_output([str(exe)]).split()]
     O = _lib.Options
-    assert got == [ctypes.sizeof(O), O.coeff_mask.offset, O.device.offset, O.epsrel_gamma.offset,
+    assert got == [ctypes.sizeof(O), O.coeff_mask.offset, O.device_plus_one.offset, O.epsrel_gamma.offset,
                    O.epsrel_heyvaerts_outer.offset, ctypes.sizeof(_lib.Extras)]
     # and as C++
     cpp = tmp_path / "layout.cpp"

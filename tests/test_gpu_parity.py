@@ -556,6 +556,59 @@ def test_device_pointer_path_and_multi_entry_agree_with_host_path():
     assert np.array_equal(multi.values, host.values, equal_nan=True) and np.array_equal(multi.status, host.status)
 
 
+def test_multi_entry_shards_over_two_gpus_bitwise():
+    """north_star's sharding path (one process, one host thread + stream per GPU, host gather): the
+    result must be bit-identical to the single-device one, odd sizes and broadcast columns included."""
+    if R.device_count() < 2:
+        pytest.skip("needs two GPUs")
+    kind, s, theta, params = R.synthetic_batch("pitchy_pl", 1001, seed=4)
+    one = R.compute_all_dimensionless_batch(kind, s, theta, params, device=0)
+    for nd in (2, 0):
+        multi = R.compute_all_dimensionless_batch(kind, s, theta, params, n_devices=nd)
+        assert np.array_equal(multi.values, one.values, equal_nan=True)
+        assert np.array_equal(multi.status, one.status)
+    # fewer points than devices
+    tiny = R.compute_all_dimensionless_batch(kind, s[:1], theta[:1], [np.asarray(p)[:1] if np.ndim(p) else p for p in params],
+                                             n_devices=2)
+    assert np.array_equal(tiny.values[:, 0], one.values[:, 0], equal_nan=True)
+
+
+def test_async_calls_on_two_streams_do_not_race():
+    """The device entry with synchronize=0 on two different streams back to back: the library's
+    per-device scratch is protected by an on-device wait on the previous call's completion event
+    (include/rimphony_b200.h), so both results must equal the synchronous ones."""
+    import torch
+    dev = torch.device("cuda", 0)
+    batches = [R.synthetic_batch("pitchy_pl", 3000, seed=21), R.synthetic_batch("pitchy_kappa", 1500, seed=22)]
+    want = [R.compute_all_dimensionless_batch(k, s, th, p, device=0) for k, s, th, p in batches]
+    streams = [torch.cuda.Stream(device=dev), torch.cuda.Stream(device=dev)]
+    outs, keep = [], []
+    for (kind, s, th, p), st in zip(batches, streams):
+        d_s, d_t = torch.from_numpy(s).to(dev), torch.from_numpy(th).to(dev)
+        d_p = [torch.from_numpy(np.atleast_1d(np.asarray(c, dtype=np.float64))).to(dev) for c in p]
+        d_out = torch.full((8 * len(s),), float("nan"), dtype=torch.float64, device=dev)
+        d_status = torch.zeros(len(s), dtype=torch.int32, device=dev)
+        keep.append((d_s, d_t, d_p))
+        outs.append((d_out, d_status))
+    torch.cuda.synchronize()
+    for (kind, s, th, p), st, (d_s, d_t, d_p), (d_out, d_status) in zip(batches, streams, keep, outs):
+        R.compute_all_dimensionless_device(kind, d_s, d_t, d_p, d_out, d_status, stream=st, synchronize=False)
+    torch.cuda.synchronize()
+    for (d_out, d_status), w in zip(outs, want):
+        assert np.array_equal(d_out.cpu().numpy().reshape(8, -1), w.values, equal_nan=True)
+        assert np.array_equal(d_status.cpu().numpy(), w.status)
+
+
+def test_calls_leave_the_current_device_alone():
+    import torch
+    if R.device_count() < 2:
+        pytest.skip("needs two GPUs")
+    torch.cuda.set_device(0)
+    kind, s, theta, params = R.synthetic_batch("powerlaw", 8, seed=2)
+    R.compute_all_dimensionless_batch(kind, s, theta, params, device=1)
+    assert torch.cuda.current_device() == 0
+
+
 def test_high_harmonic_corner_runs_and_is_finite():
     """BASELINE C4: s >= 1e5 (rel_width switch at s >= 1e6, symphony.rs:337-341)."""
     s = np.array([1e5, 3e5, 1e6, 3e6, 1e7])

@@ -41,7 +41,7 @@ def main():
     mask = int(sys.argv[1], 0) if len(sys.argv) > 1 else 0xFF
     n_tp = int(sys.argv[2]) if len(sys.argv) > 2 else 32768
     only_tp = os.environ.get("FAST_CHECK_ONLY_THROUGHPUT") == "1"
-    for name in (() if only_tp else ("pitchy_pl", "symphony_rows", "powerlaw", "pitchy_kappa", "juettner_sweep", "pitchy_pl_4k")):
+    for name in (() if only_tp else ("pitchy_pl", "symphony_rows", "powerlaw", "pitchy_kappa", "juettner_sweep", "pitchy_pl_4k", "pitchy_pl_10k", "pitchy_kappa_10k", "powerlaw_10k")):
         path = os.path.join(ROOT, "tests", "golden", name + ".npz")
         if not os.path.exists(path):
             continue
