@@ -424,6 +424,27 @@ struct PanelStack {
         sp++;
     }
     RB_FN void seal() const { warp_fence(); } // make pushes visible before the next pop
+    // reverse the order of the pending panels (the first one pushed is then popped first)
+    RB_FN void reverse(const Warp &w)
+    {
+        warp_fence();
+#ifdef RB_DEVICE_BUILD
+        if (w.lane == 0)
+#endif
+        {
+            for (int i = 0, j = sp - 1; i < j; i++, j--) {
+                const double a = lv->stk_a[i], b = lv->stk_b[i];
+                const int g = lv->stk_tag[i];
+                lv->stk_a[i] = lv->stk_a[j];
+                lv->stk_b[i] = lv->stk_b[j];
+                lv->stk_tag[i] = lv->stk_tag[j];
+                lv->stk_a[j] = a;
+                lv->stk_b[j] = b;
+                lv->stk_tag[j] = g;
+            }
+        }
+        warp_fence();
+    }
     RB_FN void pop(double &a, double &b, int &tag)
     {
         sp--;

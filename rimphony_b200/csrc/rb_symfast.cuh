@@ -34,6 +34,7 @@ constexpr double kPeakSpan = 2.6;    // seed half-width in units of n^(-1/3): ex
 constexpr double kGrade = 0.875;     // low n: the central panels are cut again at this fraction of the first cut
 constexpr double kUncutSplit = 0.5;  // a side without cuts is seeded as two panels, split at this fraction of the span
 constexpr double kLightChunk = 1e-3; // a chunk after one that added less than this fraction gets the 7-point rule
+constexpr double kLightGammaTolerance = 10.0; // gamma integrals of a light chunk: this times epsrel_gamma
 constexpr double kInnerFloor = 1.0; // acceptance floor of a gamma panel, fraction of the integral so far
 constexpr double kPanelWidth = 2.302585092994046; // outer panel width in u = ln n (one decade)
 constexpr int kMaxChunks = 400;   // safety net of the chunk loop (the reference has none)
@@ -185,7 +186,8 @@ RB_FN void sym_node(const SymFastCtx<KIND> &cx, double n, double gamma, double (
 // ((+) = gamma > gamma_peak, symphony.rs:356-363), multiplied by wa / wb and
 // parked in column `col` of the outer tile (A rows / B rows).
 template <int KIND>
-RB_FN_NOINLINE void sym_gamma_integral(Warp &w, const SymFastCtx<KIND> &cx, double n, int col, double wa, double wb)
+RB_FN_NOINLINE void sym_gamma_integral(Warp &w, const SymFastCtx<KIND> &cx, double n, int col, double wa, double wb,
+                                       bool light = false)
 {
     SymFastWS &ws = *cx.ws;
     const double s = cx.s, costh = cx.cos_th, sinth = cx.sin_th;
@@ -256,7 +258,13 @@ RB_FN_NOINLINE void sym_gamma_integral(Warp &w, const SymFastCtx<KIND> &cx, doub
     // yet small (n <~ 1000), as a guard for the mildly relativistic regime.
     const bool keep_remainders = !full && !(span < kTailSkipSpan);
     double cut[2][2]; // [side][which]: 0 < |cut0| <= |cut1| <= span, or == span when absent
-    {
+    // A chunk far up the tail (`light`: the previous one added less than kLightChunk of the sum) needs
+    // its gamma integrals to ~1 %: one 15-point panel per side of the peak, no cuts at the expansion
+    // boundaries, ten times the tolerance.  1 % of < 1e-3 of the coefficient is inside its tolerance
+    // and the stop rule |chunk| < |sum| / 1e5 does not notice it.
+    if (light) {
+        cut[0][0] = cut[0][1] = cut[1][0] = cut[1][1] = span;
+    } else {
         const bool leung = n >= kNJn;
         warp_fence(); // orders prepared by lane 0
         const double lo = ws.on.lo_minus, hi = ws.on.hi_minus;
@@ -382,7 +390,7 @@ RB_FN_NOINLINE void sym_gamma_integral(Warp &w, const SymFastCtx<KIND> &cx, doub
         stk.push(w, -1.0, -span, 0);
         stk.push(w, span, 1.0, 1);
     }
-    const bool graded = full || keep_remainders;
+    const bool graded = (full || keep_remainders) && !light;
     if (graded) {
 #pragma unroll 1
         for (int side = 0; side < 2; side++) {
@@ -402,6 +410,10 @@ RB_FN_NOINLINE void sym_gamma_integral(Warp &w, const SymFastCtx<KIND> &cx, doub
             if (!(c0 < span)) { // no cut on this side: two halves instead of one wide panel
                 lo = (which == 0) ? span : ((which == 1) ? kUncutSplit * span : 0.0);
                 hi = (which == 0) ? span : ((which == 1) ? span : kUncutSplit * span);
+                if (light) { // ... or the whole side as one
+                    lo = (which == 2) ? 0.0 : span;
+                    hi = span;
+                }
             }
             if (graded && which == 2 && c0 < span)
                 hi = kGrade * c0;
@@ -466,7 +478,8 @@ RB_FN_NOINLINE void sym_gamma_integral(Warp &w, const SymFastCtx<KIND> &cx, doub
             RB_FOR_CHAN(c, 6)
             {
                 big[c] = fmax(big[c], fabs(r[c]));
-                ok[c] = panel_ok(r[c], e[c], cx.epsrel_gamma, kInnerFloor * fmax(est[c] + fabs(r[c]), big[c]));
+                ok[c] = panel_ok(r[c], e[c], light ? kLightGammaTolerance * cx.epsrel_gamma : cx.epsrel_gamma,
+                                 kInnerFloor * fmax(est[c] + fabs(r[c]), big[c]));
             }
             const bool accept = chan_all(ok, 6);
 #ifdef RB_TRACE_INNER
@@ -788,7 +801,6 @@ RB_FN void symphony_point_fast(Warp &w, const Dist &dist, double s, double theta
         warp_fence();
         tile_clear(w, ws.outer.tile);
         int filled = 0;
-
         while (stk.sp > 0) {
             double ua, ub;
             int tag;
@@ -809,7 +821,7 @@ RB_FN void symphony_point_fast(Warp &w, const Dist &dist, double s, double theta
 #pragma unroll 1
             for (int j = 0; j < n_nodes; j++) {
                 const double n = rb_exp(uc + uhl * rx[j]);
-                sym_gamma_integral<KIND>(w, cx, n, tile_col(j), rwk[j] * n, rwd[j] * n);
+                sym_gamma_integral<KIND>(w, cx, n, tile_col(j), rwk[j] * n, rwd[j] * n, light);
             }
             warp_fence();
             PerChan<double> r, e;
@@ -835,6 +847,9 @@ RB_FN void symphony_point_fast(Warp &w, const Dist &dist, double s, double theta
             }
         }
 
+#ifdef RB_TRACE_CHUNK
+        RB_TRACE_CHUNK(chunk_no, light, n_lo_chunk, delta_n, chunk, tail, disc, w.n_apply_lanes);
+#endif
         if (n_lo_chunk >= kSensitiveN && s < 1e6) {
             // Fidelity guard, per accumulator: one whose chunks up here still matter leaves this
             // path (it is the emission coefficients of hard spectra, as a rule; absorption and

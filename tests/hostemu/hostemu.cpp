@@ -11,6 +11,24 @@
 #include <cstring>
 #include <vector>
 
+// The chunk-growth vote of the Symphony product path (rb_symfast.cuh: delta_n grows when ALL active
+// accumulators ask for it, whereas the reference grows it per coefficient, symphony.rs:243-258):
+// count the votes and those in which the accumulators disagreed.
+static long g_votes = 0, g_split_votes = 0;
+#define RB_TRACE_VOTE(chunk_no, n_lo, delta_n, active, grow)                                   \
+    do {                                                                                       \
+        int na_ = 0, ng_ = 0;                                                                  \
+        for (int c_ = 0; c_ < 8; c_++)                                                         \
+            if (active.v[c_]) {                                                                \
+                na_++;                                                                         \
+                if (grow.v[c_])                                                                \
+                    ng_++;                                                                     \
+            }                                                                                  \
+        g_votes++;                                                                             \
+        if (ng_ != 0 && ng_ != na_)                                                            \
+            g_split_votes++;                                                                   \
+    } while (0)
+
 #include "../../rimphony_b200/csrc/rb_symphony.cuh"
 #include "../../rimphony_b200/csrc/rb_heyvaerts.cuh"
 #include "../../rimphony_b200/csrc/rb_symfast.cuh"
@@ -19,6 +37,12 @@
 using namespace rb;
 
 extern "C" {
+
+void emu_vote_stats(long *out2)
+{
+    out2[0] = g_votes;
+    out2[1] = g_split_votes;
+}
 
 double emu_leung_j(double n, double x)
 {

@@ -10,16 +10,14 @@ integration tolerance, with sign agreement on rho_Q/V and alpha_V"):
   knife-edge cases described at FAITHFUL_NAN_SLACK.
 * FAST mode (the product default) integrates the same integrands over the same domains with
   the same truncation rules, but organises the quadrature differently (rb_symfast.cuh,
-  rb_heyfast.cuh).  Its own quadrature error is ~1e-5 (test_fast_mode_is_converged); what
-  separates it from the oracle is the REFERENCE's integration noise (nested QAG at epsrel =
-  1e-3, symphony.rs:266, 376; heyvaerts.rs:206-274).  The bar:
-    - j_I, alpha_I, j_Q, alpha_Q: <= 1e-3 relative on >= 99.8 % of points (>= 99 % on the
-      200-point sets), <= 2e-2 on all, same NaN pattern, same sign;
-    - Stokes V: |gpu - oracle| <= 1e-3 (|lobe+| + |lobe-|) on >= 99.8 %, <= 5e-3 on all;
-    - rho_Q, rho_V for s sin(theta) >= 1: <= 1e-3 on >= 99 %, <= 2e-2 on all, same sign;
-      below 1 the Heyvaerts expansions are outside their range, the reference returns NaN
-      for most points and sequence-dependent values for the rest: finite pairs must agree
-      to 1e-3 on >= 70 % (exact reproduction there is what MODE_FAITHFUL is for).
+  rb_heyfast.cuh).  Its own quadrature error is ~1e-5 (test_fast_mode_is_converged).  The bar is
+  the north-star one: <= 1e-3 (Stokes V: of |lobe+| + |lobe-|) on >= 99.9 % of the points, NaN
+  pattern on >= 99.9 %, same signs, over the entries where the reference's own algorithm is
+  defined to 1e-3 (rimphony_b200/parity.py; the excluded entries are counted and bounded).
+  Exception, documented in tests/golden/heyvaerts_low_s.md: rho_Q / rho_V of the power laws at
+  s < 1, where the reference's NaN verdict is a property of its tolerance; the test asserts the
+  measured agreement of the reference-divergence rule there (>= 85 % of the verdicts, >= 97 % of
+  the pairs that are finite on both sides within 1e-3).
 * FUSED mode keeps the reference's control flow on shared nodes.  Both it and
   the reference then carry an independent integration error of up to the QAG tolerance
   (epsrel = 1e-3 per nested level, symphony.rs:266, 376), so the bar is
@@ -40,7 +38,6 @@ pytestmark = pytest.mark.gpu
 
 NAMES = R.COEFFICIENT_NAMES
 FIXTURES = ["pitchy_pl", "powerlaw", "pitchy_kappa", "symphony_rows"]
-FAST_FIXTURES = FIXTURES + ["pitchy_pl_4k", "pitchy_kappa_2k", "pitchy_pl_high_s"]
 
 
 def run(fx, mode, mask=0xFF, extras=True, **kw):
@@ -229,60 +226,83 @@ def test_fused_mode_within_the_integration_tolerance(golden, name):
 
 
 # --- the hot path: fast mode (the product default) -----------------------------------------
+#
+# The bar is BASELINE.json's: <= 1e-3 relative (Stokes V: of the lobe scale) on >= 99.9 % of the
+# points, the reference's NaN pattern on >= 99.9 %, no sign difference.  Entries where the
+# reference's own algorithm is not defined to 1e-3 (its value moves by more than that, or its NaN
+# flips, when its tolerance goes from 1e-3 to 3e-4 or s is nudged by 1e-9: the *_stability.npz
+# companions, tests/golden/make_stability.py) are excluded and counted (rimphony_b200/parity.py).
+# One documented exception: rho_Q / rho_V of the power laws at s < 1, where the reference's NaN is a
+# property of its tolerance (tests/golden/heyvaerts_low_s.md); there the test asserts the measured
+# agreement of the reference-divergence rule instead.
 
-@pytest.mark.parametrize("name", FAST_FIXTURES)
-def test_fast_mode_within_the_integration_tolerance(golden, name):
-    fx = golden(name)
-    res = run(fx, R.MODE_FAST)
-    want, lobes = fx["out"], fx["lobes"]
+def _fast_stats(name, mask=0xFF, rows=None):
+    from rimphony_b200 import parity as P
+    fx = P.load_fixture(name)
+    res = R.compute_all_dimensionless_batch(int(fx["kind"]), fx["s"], fx["theta"], list(fx["params"]), coeff_mask=mask,
+                                            extras=True)
+    sel = slice(None) if rows is None else rows
+    stats = P.parity_stats(res.values[:, sel], fx["out"][:, sel], fx["lobes"][:, sel], fx["defined"][:, sel], mask=mask)
+    return fx, res, stats
+
+
+@pytest.mark.parametrize("name", ["pitchy_pl_4k", "pitchy_pl_10k", "powerlaw_10k", "pitchy_kappa_2k", "pitchy_kappa_10k"])
+def test_fast_mode_meets_the_north_star_bar(name):
+    import os
+    from rimphony_b200 import parity as P
+    if not os.path.exists(os.path.join(P.GOLDEN_DIR, name + ".npz")):
+        pytest.skip("fixture not generated")
+    fx, res, stats = _fast_stats(name)
     n = len(fx["s"])
-    sigma0 = fx["s"] * np.sin(fx["theta"])
-    frac = 0.998 if n >= 1000 else 0.99
+    for nm in NAMES[:6]:   # j and alpha: everywhere
+        v = stats[nm]
+        assert v["frac_within"] >= 0.999, (nm, v)
+        assert v["nan_mismatch"] <= 0.001 * n, (nm, v)
+        assert v["sign_mismatch"] == 0 or nm in ("j_V", "alpha_V"), (nm, v)
+        assert v["undefined"] <= 0.02 * n, (nm, v)
+    # Faraday: the bar holds for s >= 1 ...
+    hi = np.where(fx["s"] >= 1.0)[0]
+    st_hi = P.parity_stats(res.values[:, hi], fx["out"][:, hi], None, fx["defined"][:, hi], mask=0xC0)
+    for nm in NAMES[6:]:
+        v = st_hi[nm]
+        assert v["frac_within"] >= 0.999, (nm, v)
+        assert v["nan_mismatch"] <= 0.001 * len(hi) + 1, (nm, v)
+        assert v["sign_mismatch"] == 0, (nm, v)
+    # ... and below s = 1 (power laws only: the kappa configuration has s >= 1) the measured agreement
+    lo = np.where(fx["s"] < 1.0)[0]
+    if len(lo) >= 100:
+        st_lo = P.parity_stats(res.values[:, lo], fx["out"][:, lo], None, fx["defined"][:, lo], mask=0xC0)
+        for nm in NAMES[6:]:
+            v = st_lo[nm]
+            assert v["frac_within"] >= 0.97, (nm, v)      # finite on both sides: the same number
+            assert v["nan_mismatch"] <= 0.15 * len(lo), (nm, v)   # the verdict: 85 % at least (measured 88-93 %)
+            assert v["sign_mismatch"] == 0, (nm, v)
+        diverges = (res.status & R.STATUS_REFERENCE_DIVERGES) != 0
+        assert np.array_equal(diverges, fx["s"] < 0.38)   # the rule is a threshold on s, nothing else
+        assert np.isnan(res.values[7][diverges]).all() and np.isnan(res.values[6][fx["s"] < 0.35]).all()
+    # the fidelity guard: never on the power-law batches, a quarter of the hard kappa spectra
     rerouted = (res.status & R.STATUS_REROUTED) != 0
-
-    for c in range(6):
-        # NaN is the reference's failure marker (Bessel derivative beyond n = 1e15, failed QAG)
-        mismatch = np.isnan(res.values[c]) != np.isnan(want[c])
-        assert mismatch.mean() <= 0.005, (NAMES[c], mismatch.sum())
-    for c in range(4):  # j_I, alpha_I, j_Q, alpha_Q
-        ok = finite_pairs(res.values[c], want[c])
-        rel = np.abs(res.values[c][ok] / want[c][ok] - 1)
-        assert (rel > 1e-3).sum() <= max(1, (1 - frac) * ok.sum()), (NAMES[c], (rel <= 1e-3).mean())
-        # the tail of this distribution is the reference's noise, e.g. 1.0e-2 on j_Q at theta = 0.009
-        # (pitchy_kappa_2k point 1950) where FAST at 1e-6 tolerances reproduces FAST to 1e-6
-        assert rel.max() <= 2e-2, (NAMES[c], rel.max())
-        assert (np.sign(res.values[c][ok]) == np.sign(want[c][ok])).all()
-    for c, (lp, lm) in ((4, (0, 1)), (5, (2, 3))):  # Stokes V against the lobe scale
-        ok = finite_pairs(res.values[c], want[c])
-        scale = np.abs(lobes[lp]) + np.abs(lobes[lm])
-        err = np.abs(res.values[c] - want[c])[ok] / scale[ok]
-        assert (err > 1e-3).sum() <= max(1, (1 - frac) * ok.sum()), (NAMES[c], (err <= 1e-3).mean())
-        assert err.max() <= 5e-3, (NAMES[c], err.max())
-        resolved = ok & (np.abs(want[c]) > 1e-2 * scale)
-        assert (np.sign(res.values[c][resolved]) == np.sign(want[c][resolved])).all()
-    # points handed to the faithful sequence: the chunks below n = 1e9 come from the product path
-    # (its ~1e-5), the ones above from the reference's exact rule sequence
-    if rerouted.any():
-        for c in range(4):
-            ok = finite_pairs(res.values[c], want[c]) & rerouted
-            assert np.abs(res.values[c][ok] / want[c][ok] - 1).max() < 1e-3, NAMES[c]
-    # the power-law batches never need the guard; hard kappa spectra do
     if fx["kind"] in (R.POWER_LAW, R.PITCHY_PL):
         assert rerouted.mean() <= 0.002
 
-    for c in (6, 7):  # Faraday
-        hi = sigma0 >= 1.0
-        ok = finite_pairs(res.values[c], want[c]) & hi
-        rel = np.abs(res.values[c][ok] / want[c][ok] - 1)
-        assert (rel > 1e-3).sum() <= max(1, 0.01 * ok.sum()), (NAMES[c], (rel <= 1e-3).mean())
-        assert rel.max() <= 2e-2, (NAMES[c], rel.max())
-        assert (np.sign(res.values[c][ok]) == np.sign(want[c][ok])).all()
-        mismatch = (np.isnan(res.values[c]) != np.isnan(want[c])) & hi
-        assert mismatch.sum() <= 2 + 0.02 * hi.sum(), (NAMES[c], mismatch.sum())
-        lo = finite_pairs(res.values[c], want[c]) & ~hi
-        if lo.sum() >= 20:
-            rel = np.abs(res.values[c][lo] / want[c][lo] - 1)
-            assert (rel <= 1e-3).mean() >= 0.7, (NAMES[c], (rel <= 1e-3).mean())
+
+@pytest.mark.parametrize("name", ["pitchy_pl", "powerlaw", "pitchy_kappa", "symphony_rows", "pitchy_pl_high_s"])
+def test_fast_mode_small_fixtures(golden, name):
+    """The 64-400-point sets (no stability companions): at most one entry per coefficient beyond 1e-3 on j / alpha,
+    rho for s >= 1 within 1e-3 up to two entries."""
+    from rimphony_b200 import parity as P
+    fx = golden(name)
+    res = run(fx, R.MODE_FAST)
+    stats = P.parity_stats(res.values, fx["out"], fx["lobes"], None)
+    for nm in NAMES[:6]:
+        v = stats[nm]
+        assert v["finite"] - v["within"] <= 1 and v["nan_mismatch"] <= 1, (nm, v)
+        assert v["max_err"] <= 1e-2, (nm, v)
+    hi = fx["s"] >= 1.0
+    st_hi = P.parity_stats(res.values[:, hi], fx["out"][:, hi], None, None, mask=0xC0)
+    for nm in NAMES[6:]:
+        v = st_hi[nm]
+        assert v["finite"] - v["within"] <= 2 and v["nan_mismatch"] <= 2 and v["sign_mismatch"] == 0, (nm, v)
 
 
 def test_fast_mode_juettner_faraday_sweep(golden):
