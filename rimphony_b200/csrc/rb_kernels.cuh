@@ -143,11 +143,26 @@ __global__ void __launch_bounds__(kThreadsPerBlock, 4) k_symphony_diag(BatchArgs
 constexpr int kFastWarps = RB_FAST_WARPS;
 constexpr int kFastThreads = kFastWarps * 32;
 static_assert(RB_LOCKSTEP != 2 || kFastWarps % 4 == 0, "per-scheduler lock-step groups need a multiple of four warps");
+// Lock-step bookkeeping of a CTA (cohort mode keeps two counters in shared memory).
+__device__ __forceinline__ void lockstep_init()
+{
+#if RB_LOCKSTEP == 4
+    if (threadIdx.x == 0) {
+        g_lockstep_state[0] = 0;
+        g_lockstep_state[1] = 0;
+    }
+    __syncthreads();
+#endif
+}
 
-// After its last point a warp keeps the lock-step barrier company until its whole group is idle.
+// After its last point: barrier modes keep the barrier company until the whole group is idle; cohort
+// mode just counts the warp out.
 __device__ __forceinline__ void lockstep_drain()
 {
-#if RB_LOCKSTEP
+#if RB_LOCKSTEP == 4
+    if ((threadIdx.x & 31) == 0)
+        atomicAdd(&g_lockstep_state[1], 1);
+#elif RB_LOCKSTEP
     while (lockstep_tick(true) != lockstep_group_threads()) {
     }
 #endif
@@ -158,6 +173,7 @@ template <int KIND>
 __global__ void __launch_bounds__(kFastThreads, RB_FAST_BLOCKS) k_symphony_fast(BatchArgs a)
 {
     extern __shared__ double smem[];
+    lockstep_init();
     const int warp = threadIdx.x >> 5;
     SymFastWS &ws = reinterpret_cast<SymFastWS *>(smem)[warp];
     Warp w;
@@ -274,6 +290,7 @@ template <int KIND>
 __global__ void __launch_bounds__(kFastThreads, RB_FAST_BLOCKS) k_heyvaerts_fast(BatchArgs a)
 {
     extern __shared__ double smem[];
+    lockstep_init();
     const int warp = threadIdx.x >> 5;
     HeyFastWS &ws = reinterpret_cast<HeyFastWS *>(smem)[warp];
     Warp w;

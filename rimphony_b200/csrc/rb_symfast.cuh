@@ -230,7 +230,9 @@ RB_FN_NOINLINE void sym_gamma_integral(Warp &w, const SymFastCtx<KIND> &cx, doub
         }
     }
 
+#ifndef RB_LOCKSTEP_NOSEED
     lockstep_tick(); // a seeding tick
+#endif
     warp_fence();
 #ifdef RB_DEVICE_BUILD
     if (w.lane < 2) // orders n and n + 1 side by side

@@ -262,7 +262,7 @@ int launch_kind(DeviceContext &c, BatchArgs a, const ResolvedOptions &o, cudaStr
 
     RB_CUDA(cudaMemsetAsync(counters, 0, 4 * sizeof(unsigned long long), st));
     RB_CUDA(cudaEventRecord(c.ev[0], st));
-    a.hey_free_below = (KIND == kDistPowerLaw || KIND == kDistPitchyPL) ? kHeyRefDivergesQ : 0.0;
+    a.hey_free_below = (KIND == kDistPitchyPL) ? kHeyDivQLo : ((KIND == kDistPowerLaw) ? 0.05 : 0.0);
 
     // 1. normalisation (+ the cost-ordered schedule of the product kernels)
     if (stage_normalize<KIND>(a, c.sm_count, st))

@@ -45,9 +45,11 @@ def main():
     t1 = time.time()
     nudge, nudge_lobes = O.batch(kind, s * (1.0 + NUDGE), theta, params, coeff_mask=mask)
     t2 = time.time()
-    np.savez_compressed(os.path.join(HERE, name + "_stability.npz"), tight=tight, nudge=nudge,
-                        tight_lobes=tight_lobes, nudge_lobes=nudge_lobes,
-                        tight_epsrel=TIGHT, nudge_rel=NUDGE, mask=mask)
+    path = os.path.join(HERE, name + "_stability.npz")
+    keep = dict(np.load(path)) if os.path.exists(path) else {}   # e.g. the `converged` arrays of make_converged.py
+    keep.update(tight=tight, nudge=nudge, tight_lobes=tight_lobes, nudge_lobes=nudge_lobes, tight_epsrel=TIGHT,
+                nudge_rel=NUDGE, mask=mask)
+    np.savez_compressed(path, **keep)
     print(f"{name}: tight {t1 - t0:.0f} s, nudge {t2 - t1:.0f} s")
     base = fx["out"]
     for c in range(8):

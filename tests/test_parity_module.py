@@ -51,8 +51,9 @@ def test_fixture_with_stability_companion_loads():
     fx = P.load_fixture("pitchy_pl_4k")
     assert fx["defined"].shape == fx["out"].shape and fx["stability_mask"] == 0xC0
     frac = 1 - fx["defined"][6:].mean()
-    assert 0.005 < frac < 0.05          # 1.6-2.2 % of the rho entries (tests/golden/heyvaerts_low_s.md)
-    assert fx["defined"][:6].all()
+    assert 0.005 < frac < 0.05          # 1.7-2.4 % of the rho entries (tests/golden/heyvaerts_low_s.md)
+    # j / alpha: only the handful of entries where the reference's own error exceeds 1e-3 (make_converged.py)
+    assert fx["converged_entries"] > 0 and (~fx["defined"][:6]).sum() <= 0.001 * fx["defined"][:6].size
 
 
 def test_sampler_prefix_is_independent_of_the_batch_size():
@@ -106,14 +107,21 @@ def _emu_rho(lib, kind, params, s, theta):
 
 
 def test_reference_divergence_rule_on_the_host_build(emu_lib):
-    """rb_heyfast.cuh kHeyRefDivergesQ/V: the power laws with gamma_min = 1 return NaN for rho below
-    s = 0.35 / 0.38 with STATUS_REFERENCE_DIVERGES and no rule application; other kinds, and a power
-    law with gamma_min > 1, integrate."""
+    """rb_heyfast.cuh kHeyRefDiverges*: the power laws with gamma_min = 1 return NaN for rho_V below
+    s = 0.38 (0.33 isotropic) and for rho_Q below a threshold that rises with theta (0.18 ... 0.37; 0 ... 0.30
+    isotropic), with STATUS_REFERENCE_DIVERGES and no rule application where both are NaN; other kinds, and a
+    power law with gamma_min > 1, integrate."""
     pl = [2.5, 1.0, 1.0, 1e12, 1e10]
     q, v, apps, status = _emu_rho(emu_lib, R.PITCHY_PL, pl, 0.2, 0.9)
     assert np.isnan(q) and np.isnan(v) and apps == 0 and status & R.STATUS_REFERENCE_DIVERGES
-    q, v, apps, status = _emu_rho(emu_lib, R.PITCHY_PL, pl, 0.365, 0.9)
+    q, v, apps, status = _emu_rho(emu_lib, R.PITCHY_PL, pl, 0.375, 0.9)
     assert np.isfinite(q) and np.isnan(v) and apps > 0 and status & R.STATUS_REFERENCE_DIVERGES
+    q, v, apps, status = _emu_rho(emu_lib, R.PITCHY_PL, pl, 0.25, 0.1)     # small angle: rho_Q is computed
+    assert np.isfinite(q) and np.isnan(v) and apps > 0
+    q, v, apps, status = _emu_rho(emu_lib, R.POWER_LAW, [2.5, 1.0, 1e12, 1e10], 0.25, 0.3)
+    assert np.isfinite(q) and np.isnan(v) and status & R.STATUS_REFERENCE_DIVERGES
+    q, v, apps, status = _emu_rho(emu_lib, R.POWER_LAW, [2.5, 1.0, 1e12, 1e10], 0.25, 1.4)
+    assert np.isnan(q) and np.isnan(v) and apps == 0
     q, v, apps, status = _emu_rho(emu_lib, R.PITCHY_PL, pl, 0.7, 0.9)
     assert np.isfinite(q) and np.isfinite(v) and not status & R.STATUS_REFERENCE_DIVERGES
     q, v, apps, status = _emu_rho(emu_lib, R.POWER_LAW, [2.5, 1.5, 1e12, 1e10], 0.2, 0.9)
