@@ -80,6 +80,10 @@ RB_HD double hey_ref_diverges_q(bool isotropic, double sin_th, double cos_th)
 
 struct HeyFastWS {
     EngLevel inner, outer;
+    // the warp-uniform context of the point in work, in shared memory rather than on the kernel's stack
+    // (see SymFastWS)
+    Dist dist;
+    double ctx_store[10];
 };
 
 template <int KIND>
@@ -580,8 +584,11 @@ template <int KIND>
 RB_FN void heyvaerts_point_fast(Warp &w, const Dist &dist, double s, double theta, double epsrel_inner,
                                 double epsrel_outer, HeyFastWS &ws, double (&out2)[2])
 {
-    HeyFastCtx<KIND> cx;
-    cx.d = &dist;
+    static_assert(sizeof(HeyFastCtx<KIND>) <= sizeof(ws.ctx_store), "context store too small");
+    warp_fence();
+    HeyFastCtx<KIND> &cx = *reinterpret_cast<HeyFastCtx<KIND> *>(ws.ctx_store);
+    ws.dist = dist; // every lane stores the same values
+    cx.d = &ws.dist;
     cx.ws = &ws;
     cx.g.cos_th = cos(theta);
     cx.g.sin_th = sin(theta);
@@ -589,6 +596,7 @@ RB_FN void heyvaerts_point_fast(Warp &w, const Dist &dist, double s, double thet
     cx.g.sigma0_sq = cx.g.sigma0 * cx.g.sigma0;
     cx.epsrel_inner = epsrel_inner;
     cx.epsrel_outer = epsrel_outer;
+    warp_fence();
     const double sigma0 = cx.g.sigma0;
 
     PerChan<bool> alive;

@@ -48,7 +48,10 @@ constexpr int kMaxChunks = 400;   // safety net of the chunk loop (the reference
 // points (hard kappa spectra) are not computed here: they are flagged and re-run with the
 // reference's exact sequence of rule applications (MODE_FAITHFUL kernel).
 constexpr double kSensitiveN = 5e9;
-constexpr double kSensitiveFraction = 2e-4;
+#ifndef RB_SENSITIVE_FRACTION
+#define RB_SENSITIVE_FRACTION 5e-4 // per chunk; the chunks above decay at least like 1/2 per decade: < 1e-3 in all
+#endif
+constexpr double kSensitiveFraction = RB_SENSITIVE_FRACTION;
 // A flagged point does not start over: up to n ~ 1e9 the reference's quadrature is sound and
 // the product path reproduces it, so the faithful sequence resumes from the chunk-loop state
 // recorded at the first chunk starting beyond kHandoverN (s >= 10, where the chunk sequence
@@ -69,6 +72,11 @@ struct SymFastWS {
     EngLevel inner, outer;
     LeungOrder on, on1;
     double snap[kSnapDoubles];
+    // the warp-uniform context of the point in work (SymFastCtx + the distribution): in shared memory, not
+    // on the stack of the kernel, because the out-of-line quadrature functions read it through a reference
+    // and the L1 left beside 214 KB of shared memory does not hold 640 stacks
+    Dist dist;
+    double ctx_store[8];
 };
 
 // Warp-uniform context of one point.
@@ -634,13 +642,17 @@ RB_FN void symphony_point_fast(Warp &w, const Dist &dist, double s, double theta
 {
     constexpr double kNMax = 30.0, kTolerance = 1e5;
 
-    SymFastCtx<KIND> cx;
-    cx.d = &dist;
+    static_assert(sizeof(SymFastCtx<KIND>) <= sizeof(ws.ctx_store), "context store too small");
+    warp_fence();
+    SymFastCtx<KIND> &cx = *reinterpret_cast<SymFastCtx<KIND> *>(ws.ctx_store);
+    ws.dist = dist; // every lane stores the same values
+    cx.d = &ws.dist;
     cx.ws = &ws;
     cx.s = s;
     cx.cos_th = cos(theta);
     cx.sin_th = sin(theta);
     cx.epsrel_gamma = epsrel_gamma;
+    warp_fence();
 
     const double n_minus = s * fabs(cx.sin_th);
     const long long n_lo = (long long)(n_minus + 1.0);

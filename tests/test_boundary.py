@@ -210,3 +210,17 @@ def test_high_frequency_approximations_known_answers():
     # array arguments evaluate a batch
     q = pl.compute_dimensionless(C.Faraday, S.Q, np.array([1e3, 1e4]), 0.25 * math.pi)
     assert q.shape == (2,) and q[1] == pytest.approx(1.81e-9, rel=0.01)
+
+
+def test_rust_facade_declares_the_same_abi():
+    """rust/ cannot be compiled in this image (no rustc); what can be checked is that its extern "C" block
+    names exactly the symbols of the header and that its Options struct has the header's fields in order."""
+    import re
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    ffi = open(os.path.join(root, "rust", "src", "ffi.rs")).read()
+    declared = set(re.findall(r"pub fn (rimphony_b200_\w+)", ffi))
+    assert declared == set(_lib.EXPORTED_SYMBOLS)
+    fields = re.findall(r"pub (\w+): ", ffi.split("pub struct Options")[1].split("}")[0])
+    assert fields == [name for name, _ in _lib.Options._fields_]
+    header = open(os.path.join(root, "include", "rimphony_b200.h")).read()
+    assert "ABI_VERSION 2" in header and "ABI version 2" in ffi
