@@ -34,7 +34,8 @@ constexpr double kPeakSpan = 2.6;    // seed half-width in units of n^(-1/3): ex
 constexpr double kGrade = 0.875;     // low n: the central panels are cut again at this fraction of the first cut
 constexpr double kUncutSplit = 0.5;  // a side without cuts is seeded as two panels, split at this fraction of the span
 constexpr double kLightChunk = 1e-3; // a chunk after one that added less than this fraction gets the 7-point rule
-constexpr double kLightGammaTolerance = 10.0; // gamma integrals of a light chunk: this times epsrel_gamma
+constexpr double kLightGammaTolerance = 100.0; // gamma integrals of a light chunk: this times epsrel_gamma (10 %:
+                                              // the one 15-point panel per side is refined only if it is garbage)
 constexpr double kInnerFloor = 1.0; // acceptance floor of a gamma panel, fraction of the integral so far
 constexpr double kPanelWidth = 2.302585092994046; // outer panel width in u = ln n (one decade)
 constexpr int kMaxChunks = 400;   // safety net of the chunk loop (the reference has none)
@@ -269,9 +270,9 @@ RB_FN_NOINLINE void sym_gamma_integral(Warp &w, const SymFastCtx<KIND> &cx, doub
     const bool keep_remainders = !full && !(span < kTailSkipSpan);
     double cut[2][2]; // [side][which]: 0 < |cut0| <= |cut1| <= span, or == span when absent
     // A chunk far up the tail (`light`: the previous one added less than kLightChunk of the sum) needs
-    // its gamma integrals to ~1 %: one 15-point panel per side of the peak, no cuts at the expansion
-    // boundaries, ten times the tolerance.  1 % of < 1e-3 of the coefficient is inside its tolerance
-    // and the stop rule |chunk| < |sum| / 1e5 does not notice it.
+    // its gamma integrals to a few per cent: one 15-point panel per side of the peak, no cuts at the
+    // expansion boundaries, a hundred times the tolerance.  A few per cent of < 1e-3 of the coefficient is
+    // inside its tolerance and the stop rule |chunk| < |sum| / 1e5 does not notice it.
     if (light) {
         cut[0][0] = cut[0][1] = cut[1][0] = cut[1][1] = span;
     } else {
@@ -759,6 +760,14 @@ RB_FN void symphony_point_fast(Warp &w, const Dist &dist, double s, double theta
         warp_fence();
         PerChan<double> deriv, unused2;
         tile_reduce(ws.outer.tile, kEngChan, 1.0, deriv, unused2);
+        // G at the start of the chunk, from the same two probes: columns 0 and 1 hold -G(n - dn) / (2 dn) and
+        // G(n + dn) / (2 dn)
+        PerChan<double> g_start;
+        RB_FOR_CHAN(c, kEngChan)
+        {
+            const double *ot = ws.outer.tile;
+            g_start[c] = kDerivStep * n_lo_chunk * (ot[c * kEngRow + tile_col(1)] - ot[c * kEngRow + tile_col(0)]);
+        }
         PerChan<bool> grow_c;
         RB_FOR_CHAN(c, kEngChan)
         {
@@ -806,10 +815,21 @@ RB_FN void symphony_point_fast(Warp &w, const Dist &dist, double s, double theta
         // far up the tail, where the previous chunk added less than kLightChunk of the sum, the
         // 7-point rule is plenty for a decade of a power law (and 1e-3 of such a chunk is
         // far inside the tolerance)
+        // ... or, without waiting for a chunk to say so: past the maximum |G| falls, so |G(n_start)| delta_n bounds
+        // the chunk from above; when that bound is below kLightChunk of the sum the chunk is minor already
         PerChan<bool> minor;
         RB_FOR_CHAN(c, kEngChan)
         {
-            minor[c] = !active[c] || (contrib[c] != 0.0 && fabs(contrib[c]) < kLightChunk * fabs(disc[c] + tail[c]));
+            const double sum_c = fabs(disc[c] + tail[c]);
+            const bool falling = g_start[c] * deriv[c] < 0.0;
+            // a power-law tail G ~ n^-a (a = -d ln G / d ln n from the probe) integrates to G n / (a - 1); twice
+            // that, or the cruder |G| delta_n, whichever is smaller
+            const double a_slope = -deriv[c] * n_lo_chunk / g_start[c];
+            double bound = fabs(g_start[c]) * delta_n;
+            if (a_slope > 1.25)
+                bound = fmin(bound, 2.0 * fabs(g_start[c]) * n_lo_chunk / (a_slope - 1.0));
+            minor[c] = !active[c] || (contrib[c] != 0.0 && fabs(contrib[c]) < kLightChunk * sum_c) ||
+                       (falling && bound < kLightChunk * sum_c);
         }
         const bool light = chunk_no > 0 && chan_all(minor, kEngChan);
         warp_fence();
