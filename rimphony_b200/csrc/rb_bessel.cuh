@@ -187,10 +187,15 @@ RB_FN double exp_factor(double f_factor, double f_exp)
 RB_FN double leung_meissel_first(const LeungOrder &o, double x)
 {
     const double n = o.n;
+#ifdef RB_LEAN_MATH
+    const double z = x * o.ninv; // (the product path; the faithful kernels divide, as bessel.c does)
+    const double eps = (n - x) * o.ninv;
+#else
     const double z = x / n;
     const double eps = (n - x) / n;
+#endif
     const double Z = sqrt(eps * (1.0 + z));
-    const double U = 1.0 / (n * Z * Z * Z);
+    const double U = rb_rcp(n * Z * Z * Z);
     const double t1 = z * z;
     const double D = kMeisselTab[0];
 
@@ -210,20 +215,20 @@ RB_FN double leung_meissel_first(const LeungOrder &o, double x)
     const double vsum1 = U * (p0 + U * (p1 + U * (p2 + U * (p3 + U * (p4 + U * (p5 + U * (p6 + U * p7)))))));
 
     // "I substitute Gamma(n+1) with (n+1)*Gamma(n) in the denominator" (bessel.c:123)
-    const double factor = 1.0 / ((n + 1.0) * sqrt(Z));
+    const double factor = rb_rcp((n + 1.0) * sqrt(Z));
 
     double exp_val;
     if (eps < 1e-4 && n > 1e3) {
         const double exp2 = -n * sqrt(2.0 * eps) * eps *
                             (kMeisselTab[38] + (kMeisselTab[39] + (kMeisselTab[40] + (kMeisselTab[41] + (kMeisselTab[42] +
-                             (kMeisselTab[43] + kMeisselTab[44] * eps) * eps) * eps) * eps) * eps) * eps) / kMeisselTab[45];
+                             (kMeisselTab[43] + kMeisselTab[44] * eps) * eps) * eps) * eps) * eps) * eps) * rb_rcp(kMeisselTab[45]);
         exp_val = o.c_stirling + exp2 - vsum1;
     } else {
         double inv_zp1;
         if (Z < kMeisselTab[46])
             inv_zp1 = 1.0 + (-1.0 + (1.0 + (-1.0 + (1.0 + (-1.0 + (1.0 - Z) * Z) * Z) * Z) * Z) * Z) * Z;
         else
-            inv_zp1 = 1.0 / (1.0 + Z);
+            inv_zp1 = rb_rcp(1.0 + Z);
         exp_val = n * (rb_log(x * inv_zp1) - (1.0 - Z)) - vsum1 + o.c_std;
     }
     return exp_factor(factor, exp_val);
@@ -300,7 +305,7 @@ RB_FN double leung_debye_eps(double n, double x)
     const double poly = (e0 + (e1 + (e2 + (e3 + (e4 + (e5 + (e6 + (e7 + (e8 + (e9 + (e10 + (e11 + e12 * ez) * ez) * ez) * ez) *
                         ez) * ez) * ez) * ez) * ez) * ez) * ez) * ez) * ez;
 
-    return (lead + poly) / (kPi * t146 * kDebyeTab[52]);
+    return rb_div(lead + poly, kPi * t146 * kDebyeTab[52]);
 }
 
 // Integer order 0 <= n < 30 (the reference calls gsl_sf_bessel_Jn,

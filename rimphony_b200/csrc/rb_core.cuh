@@ -21,13 +21,14 @@
 #include <float.h>
 #include <math.h>
 #include <stdint.h>
+#include <string.h>
 
 #ifdef __CUDACC__
 #define RB_FN __device__ __forceinline__
 #define RB_HD __host__ __device__ __forceinline__
 #define RB_FN_NOINLINE static __device__ __noinline__
 #define RB_MFN_NOINLINE __device__ __noinline__
-#define RB_TABLE __constant__ const
+#define RB_TABLE static __constant__ // not const: a const table is folded into literals, and every FP64 literal costs two UMOVs
 #define RB_DEVICE_BUILD 1
 #else
 #ifndef RB_HOST_EMU
@@ -53,6 +54,151 @@ namespace rb {
 // Out-of-line double-precision transcendentals.  The product kernels are bound by instruction
 // fetch (profiles/): every inlined log/exp/cbrt costs 40-80 SASS instructions per call site, and
 // the hot loop has a dozen of them.  One shared copy each keeps the loop in the instruction cache.
+//
+// RB_LEAN_MATH (defined by the product-path translation units inst_k*_heyfast.cu / inst_k*_symfast.cu and by
+// the host harness; the QUADPACK-faithful kernels keep the CUDA library's functions): the kernels issue
+// 0.7-1.2 instructions per cycle and SM, every instruction counts the same, and ncu's source page says a
+// quarter of them is spent on IEEE-correct division (16 instructions each, 26-36 per node), on libdevice's
+// log/exp (87 / 64 instructions, two of every three of them moves of literal constants into uniform
+// registers) and on square roots.  The lean versions: division = a * rcp(b) with rcp from MUFU.RCP64H and one
+// cubic Newton step (6 instructions, <= 1.5 ulp; b = 0, |b| < 2^-1022, |b| = inf give NaN, |b| > 2^1022 gives
+// 0: no node of a quadrature rule depends on those), exp and log with their coefficients read from the
+// constant bank as instruction operands (32 / 38 instructions, <= 2 ulp).
+#if defined(RB_LEAN_MATH)
+#ifdef RB_DEVICE_BUILD
+RB_FN double rb_rcp_seed(double b)
+{
+    double r;
+    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(b));
+    return r;
+}
+#else
+// what MUFU.RCP64H returns, to 2^-23: subnormal arguments and results are flushed to zero
+inline double rb_rcp_seed(double b)
+{
+    if (b != b)
+        return b;
+    const double ab = fabs(b);
+    if (ab < DBL_MIN)
+        return copysign(INFINITY, b);
+    if (ab > 0x1p1022)
+        return copysign(0.0, b);
+    return (1.0 / b) * (1.0 + 0x1p-24);
+}
+#endif
+RB_FN double rb_rcp(double b)
+{
+    const double r = rb_rcp_seed(b);
+    double e = fma(-b, r, 1.0);
+    e = fma(e, e, e);
+    return fma(r, e, r);
+}
+RB_FN double rb_div(double a, double b) { return a * rb_rcp(b); }
+
+// exp(r) on |r| <= ln(2)/2: Taylor to r^13 (remainder 4e-18), highest power first
+RB_TABLE double EXP_POLY[14] = {1.0 / 6227020800.0, 1.0 / 479001600.0, 1.0 / 39916800.0, 1.0 / 3628800.0, 1.0 / 362880.0,
+                                1.0 / 40320.0,      1.0 / 5040.0,      1.0 / 720.0,      1.0 / 120.0,     1.0 / 24.0,
+                                1.0 / 6.0,          0.5,               1.0,              1.0};
+// log2(e), -ln(2) in two parts: read from the table like the coefficients (a literal costs two UMOVs)
+RB_TABLE double LN2_CONST[3] = {1.4426950408889634074, -6.93147180559945286227e-01, -2.31904681384629955842e-17};
+// log(m) = 2 atanh(f), f = (m - 1) / (m + 1), |f| <= 0.1716: 2 f + f^3 (2/3 + 2/5 f^2 + ... + 2/23 f^20)
+RB_TABLE double LOG_POLY[11] = {2.0 / 23.0, 2.0 / 21.0, 2.0 / 19.0, 2.0 / 17.0, 2.0 / 15.0, 2.0 / 13.0,
+                                2.0 / 11.0, 2.0 / 9.0,  2.0 / 7.0,  2.0 / 5.0,  2.0 / 3.0};
+
+RB_FN int rb_hi32(double x)
+{
+#ifdef RB_DEVICE_BUILD
+    return __double2hiint(x);
+#else
+    int64_t u;
+    memcpy(&u, &x, 8);
+    return (int)(u >> 32);
+#endif
+}
+RB_FN int rb_lo32(double x)
+{
+#ifdef RB_DEVICE_BUILD
+    return __double2loint(x);
+#else
+    int64_t u;
+    memcpy(&u, &x, 8);
+    return (int)(u & 0xffffffff);
+#endif
+}
+RB_FN double rb_from_hilo(int hi, int lo)
+{
+#ifdef RB_DEVICE_BUILD
+    return __hiloint2double(hi, lo);
+#else
+    const uint64_t u = ((uint64_t)(uint32_t)hi << 32) | (uint32_t)lo;
+    double x;
+    memcpy(&x, &u, 8);
+    return x;
+#endif
+}
+
+#ifdef RB_DEVICE_BUILD
+static __device__ __noinline__
+#else
+inline
+#endif
+double rb_exp(double x)
+{
+    // beyond +-1400 the result is 0 or inf whatever the argument (the comparisons let NaN through)
+    x = (x > 1400.0) ? 1400.0 : x;
+    x = (x < -1400.0) ? -1400.0 : x;
+    const double magic = 6755399441055744.0; // 1.5 * 2^52: the integer lands in the low word
+    double t = fma(x, LN2_CONST[0], magic);
+    const int k = rb_lo32(t);
+    t -= magic;
+    double r = fma(t, LN2_CONST[1], x);
+    r = fma(t, LN2_CONST[2], r);
+    double p = EXP_POLY[0];
+#pragma unroll
+    for (int i = 1; i < 14; i++)
+        p = fma(p, r, EXP_POLY[i]);
+    // 2^k in two factors (|k| <= 2020), so that results down to the subnormals and overflow come out right
+    const int k1 = k >> 1, k2 = k - k1;
+    p *= rb_from_hilo((k1 + 1023) << 20, 0);
+    return p * rb_from_hilo((k2 + 1023) << 20, 0);
+}
+
+#ifdef RB_DEVICE_BUILD
+static __device__ __noinline__
+#else
+inline
+#endif
+double rb_log(double x)
+{
+    int hi = rb_hi32(x);
+    // zero, negative, subnormal, infinite and NaN arguments: the library function
+    if ((unsigned)(hi - 0x00100000) >= 0x7fe00000u)
+        return log(x);
+    int e = (hi >> 20) - 1023;
+    hi = (hi & 0x000fffff) | 0x3ff00000;
+    if (hi >= 0x3ff6a09f) { // m in [sqrt(1/2), sqrt(2))
+        hi -= 0x00100000;
+        e += 1;
+    }
+    const double m = rb_from_hilo(hi, rb_lo32(x));
+    const double f = (m - 1.0) * rb_rcp(m + 1.0);
+    const double f2 = f * f;
+    double p = LOG_POLY[0];
+#pragma unroll
+    for (int i = 1; i < 11; i++)
+        p = fma(p, f2, LOG_POLY[i]);
+    const double ke = (double)e;
+    const double lm = fma(f * f2, p, f + f);
+    return fma(-ke, LN2_CONST[1], fma(-ke, LN2_CONST[2], lm));
+}
+#ifdef RB_DEVICE_BUILD
+static __device__ __noinline__ double rb_cbrt(double x) { return cbrt(x); }
+#else
+inline double rb_cbrt(double x) { return cbrt(x); }
+#endif
+#else // !RB_LEAN_MATH
+RB_FN double rb_rcp(double b) { return 1.0 / b; }
+RB_FN double rb_div(double a, double b) { return a / b; }
 #if defined(RB_DEVICE_BUILD) && !defined(RB_INLINE_MATH) // measured: +9 % sets/s over inlining
 static __device__ __noinline__ double rb_log(double x) { return log(x); }
 static __device__ __noinline__ double rb_exp(double x) { return exp(x); }
@@ -61,6 +207,7 @@ static __device__ __noinline__ double rb_cbrt(double x) { return cbrt(x); }
 RB_FN double rb_log(double x) { return log(x); }
 RB_FN double rb_exp(double x) { return exp(x); }
 RB_FN double rb_cbrt(double x) { return cbrt(x); }
+#endif
 #endif
 
 constexpr double kPi = 3.14159265358979323846264338327950288;

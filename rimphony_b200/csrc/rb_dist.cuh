@@ -94,8 +94,11 @@ RB_FN void dist_eval(const Dist &d, double gamma, double cos_xi, double &f, doub
         }
         const double g2m1 = gamma * gamma - 1.0;
         // norm gamma^-p rb_exp(-gamma/gc) / (gamma^2 beta),  gamma^2 beta = gamma sqrt(gamma^2 - 1)
-        f = d.norm * rb_exp(-d.p * rb_log(gamma) - gamma * d.inv_gamma_cutoff) / (gamma * sqrt(g2m1));
-        dfdg = -f * ((d.p + 1.0) / gamma + gamma / g2m1 + d.inv_gamma_cutoff);
+        const double sq = sqrt(g2m1);
+        const double inv = rb_rcp(gamma * sq); // 1 / (gamma^2 beta); 1 / gamma = inv sq, 1 / (gamma^2 - 1) = (inv gamma)^2
+        const double ig = inv * gamma;
+        f = d.norm * rb_exp(-d.p * rb_log(gamma) - gamma * d.inv_gamma_cutoff) * inv;
+        dfdg = -f * ((d.p + 1.0) * (inv * sq) + gamma * (ig * ig) + d.inv_gamma_cutoff);
         dfdcx = 0.0;
     } else if (KIND == kDistThermalJuettner) {
         f = d.norm * rb_exp(d.neg_inverse_t * gamma);
@@ -108,17 +111,19 @@ RB_FN void dist_eval(const Dist &d, double gamma, double cos_xi, double &f, doub
         }
         const double sin2 = (sin2_exact == sin2_exact) ? sin2_exact : 1.0 - cos_xi * cos_xi;
         const double g2m1 = gamma * gamma - 1.0;
-        f = d.norm * rb_exp(log_pitch_term(d.k, sin2) - d.p * rb_log(gamma) - gamma * d.inv_gamma_cutoff) /
-            (gamma * sqrt(g2m1));
-        dfdg = -f * ((d.p + 1.0) / gamma + gamma / g2m1 + d.inv_gamma_cutoff);
-        dfdcx = -f * d.k * cos_xi / sin2;
+        const double sq = sqrt(g2m1);
+        const double inv = rb_rcp(gamma * sq); // 1 / (gamma^2 beta); 1 / gamma = inv sq, 1 / (gamma^2 - 1) = (inv gamma)^2
+        const double ig = inv * gamma;
+        f = d.norm * rb_exp(log_pitch_term(d.k, sin2) - d.p * rb_log(gamma) - gamma * d.inv_gamma_cutoff) * inv;
+        dfdg = -f * ((d.p + 1.0) * (inv * sq) + gamma * (ig * ig) + d.inv_gamma_cutoff);
+        dfdcx = -f * d.k * rb_div(cos_xi, sin2);
     } else {
         const double sin2 = (sin2_exact == sin2_exact) ? sin2_exact : 1.0 - cos_xi * cos_xi;
         f = d.norm * rb_exp(log_pitch_term(d.k, sin2) -
                          (d.kappa + 1.0) * rb_log(1.0 + (gamma - 1.0) * d.inv_kappa_width) -
                          gamma * d.inv_gamma_cutoff);
-        dfdg = -f * ((d.kappa + 1.0) / (d.kappa * d.width + gamma - 1.0) + d.inv_gamma_cutoff);
-        dfdcx = -f * d.k * cos_xi / sin2;
+        dfdg = -f * (rb_div(d.kappa + 1.0, d.kappa * d.width + gamma - 1.0) + d.inv_gamma_cutoff);
+        dfdcx = -f * d.k * rb_div(cos_xi, sin2);
     }
 }
 

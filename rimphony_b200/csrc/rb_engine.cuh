@@ -275,7 +275,7 @@ RB_FN double quad_error(double d, double a, double hl)
     const double rabs = a * fabs(hl);
     double err = fabs(d * hl);
     if (rabs != 0.0 && err != 0.0) {
-        const double qq = 200.0 * err / rabs;
+        const double qq = 200.0 * rb_div(err, rabs);
         const double scale = qq * sqrt(qq);
         err = (scale < 1.0) ? rabs * scale : rabs;
     }
@@ -401,7 +401,7 @@ RB_FN_NOINLINE void tile_reduce(const double *tile, int nv, double hl, PerChan<d
         const double rabs = a * ahl;
         double err = fabs(d * hl);
         if (rabs != 0.0 && err != 0.0) {
-            const double qq = 200.0 * err / rabs;
+            const double qq = 200.0 * rb_div(err, rabs);
             const double scale = qq * sqrt(qq);
             err = (scale < 1.0) ? rabs * scale : rabs;
         }

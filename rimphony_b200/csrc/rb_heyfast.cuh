@@ -140,7 +140,7 @@ RB_FN_NOINLINE bool hey_inner_integral(Warp &w, const HeyFastCtx<KIND> &cx, int 
             // lower end (x -> 0, where the integrand has algebraic end-point behaviour, strongest
             // around the cusp pomega*) t is linear in x; far out it is ln sigma.
             nr_sigma_min = sigma_min;
-            const double ratio = sigma_max / sigma_min;
+            const double ratio = kInverseSqrt3 * sqrt(sigma_min);
             const double t_lo = 0.0, t_hi = rb_log(ratio + sqrt((ratio - 1.0) * (ratio + 1.0)));
             int n_seed = (int)ceil((t_hi - t_lo) / kHeyInnerWidth);
             n_seed = n_seed < 1 ? 1 : (n_seed > 8 ? 8 : n_seed);
@@ -179,8 +179,8 @@ RB_FN_NOINLINE bool hey_inner_integral(Warp &w, const HeyFastCtx<KIND> &cx, int 
                         lo = x;
                     else
                         hi = x;
-                    const double dh = -1.5 * sqrt(d) - 0.5 * big_k / sqrt(x);
-                    double xn = x - h / dh;
+                    const double dh = -1.5 * sqrt(d) - 0.5 * big_k * rb_rcp(sqrt(x));
+                    double xn = x - rb_div(h, dh);
                     if (!(xn > lo && xn < hi))
                         xn = 0.5 * (lo + hi);
                     if (fabs(xn - x) <= 1e-14 * v) {
@@ -238,7 +238,7 @@ RB_FN_NOINLINE bool hey_inner_integral(Warp &w, const HeyFastCtx<KIND> &cx, int 
             double vals[2];
             const double t = tc + thl * w.xk;
             if (which == kHeyNR) {
-                const double et = rb_exp(t), eti = 1.0 / et;
+                const double et = rb_exp(t), eti = rb_rcp(et);
                 const double sigma = nr_sigma_min * 0.5 * (et + eti);
                 const double x = nr_sigma_min * 0.5 * (et - eti);
                 HeyNRIntegrand<KIND, 2> f{cx.d, &g, v, 0};
@@ -264,7 +264,7 @@ RB_FN_NOINLINE bool hey_inner_integral(Warp &w, const HeyFastCtx<KIND> &cx, int 
             double vals[2];
             const double t = tc + thl * LANE_X[l];
             if (which == kHeyNR) {
-                const double et = rb_exp(t), eti = 1.0 / et;
+                const double et = rb_exp(t), eti = rb_rcp(et);
                 const double sigma = nr_sigma_min * 0.5 * (et + eti);
                 const double x = nr_sigma_min * 0.5 * (et - eti);
                 HeyNRIntegrand<KIND, 2> f{cx.d, &g, v, 0};

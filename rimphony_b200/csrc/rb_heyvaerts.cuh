@@ -47,8 +47,9 @@ struct HeyNode {
         pomega = pomega_;
         x = (x_exact == x_exact) ? x_exact : sqrt(sigma * sigma - pomega * pomega - g.sigma0_sq);
         const double t = g.sigma0 * g.sin_th;
-        const double gamma = (sigma - pomega * g.cos_th) / t;
-        double mu = (sigma * g.cos_th - pomega) / (t * sqrt(gamma * gamma - 1.0));
+        const double inv_t = rb_rcp(t);
+        const double gamma = (sigma - pomega * g.cos_th) * inv_t;
+        double mu = rb_div(sigma * g.cos_th - pomega, t * sqrt(gamma * gamma - 1.0));
 
         // sin^2(xi) = 1 - mu^2 = x^2 sin^2(theta) / ((sigma - pomega cos(theta))^2 - t^2) identically.
         // Where the caller knows x without cancellation (the product path's substitutions) this
@@ -60,7 +61,7 @@ struct HeyNode {
         if (x_exact == x_exact) {
             const double q = sigma - pomega * g.cos_th;
             const double xs = x * g.sin_th;
-            sin2 = xs * xs / ((q - t) * (q + t));
+            sin2 = rb_div(xs * xs, (q - t) * (q + t));
             if (sin2 <= 1.0) {
                 const double mag = sqrt(1.0 - sin2);
                 if (fabs(mu) > mag || !(mu == mu))
@@ -72,13 +73,13 @@ struct HeyNode {
 
         double f, dfdg, dfdcxi;
         dist_eval<KIND>(d, gamma, mu, f, dfdg, dfdcxi, sin2);
-        const double g_term = dfdg / t;
+        const double g_term = dfdg * inv_t;
         double mu_term = 0.0;
         if (dfdcxi != 0.0) {
             const double q = sigma - pomega * g.cos_th;
             const double r = pomega - sigma * g.cos_th;
             const double u = q * q - t * t;
-            const double dcxi_dsigma = (q * u * g.cos_th + u * r + r * t * t) / (u * sqrt(u) * q);
+            const double dcxi_dsigma = rb_div(q * u * g.cos_th + u * r + r * t * t, u * sqrt(u) * q);
             mu_term = dcxi_dsigma * dfdcxi;
         }
         dfds = g_term + mu_term;
@@ -101,18 +102,20 @@ struct HeyNRIntegrand {
         const double x_sq = nd.x * nd.x;
         const double v = s_sq - x_sq;
         const double sv = sqrt(v);
-        const double ratio = s_sq / v;
+        // powers of 1 / sqrt(v) from one reciprocal (the reference divides seven times, heyvaerts.rs:379-394)
+        const double isv = rb_rcp(sv);
+        const double iv = isv * isv, iv15 = iv * isv, iv2 = iv * iv, iv25 = iv2 * isv;
+        const double ratio = s_sq * iv;
         const double a1 = 1.0 / 8.0 - 5.0 / 24.0 * ratio;
         const double a2 = 3.0 / 128.0 - 77.0 / 576.0 * ratio + 385.0 / 3456.0 * (ratio * ratio);
-        const double xa1p = -5.0 / 12.0 * s_sq * x_sq / (v * v);
-        const double v15 = v * sv, v25 = v * v * sv;
+        const double xa1p = -5.0 / 12.0 * s_sq * x_sq * iv2;
 
-        const double t1 = (6.0 * a2 - a1 * a1 + xa1p) / sv + a1 * x_sq / v15 - x_sq * x_sq / v25 / 8.0;
-        const double t2 = (6.0 * a2 - a1 * a1) / v15;
+        const double t1 = (6.0 * a2 - a1 * a1 + xa1p) * isv + a1 * x_sq * iv15 - x_sq * x_sq * iv25 * 0.125;
+        const double t2 = (6.0 * a2 - a1 * a1) * iv15;
         const double u1 = 2.0 * t1 - g->sigma0_sq * t2;
         const double h = kPi * kInverseC * u1 * nd.dfds;
 
-        const double z = 0.5 * x_sq / v15 + (6.0 * a2 + xa1p - a1 * a1) / v + 1.5 * a1 * x_sq / (v * v);
+        const double z = 0.5 * x_sq * iv15 + (6.0 * a2 + xa1p - a1 * a1) * iv + 1.5 * a1 * x_sq * iv2;
         const double f = -2.0 * kPi * kInverseC * z * pomega * nd.dfds;
 
         if constexpr (NV == 2) {
@@ -139,8 +142,9 @@ struct HeyQRIntegrand {
         const double x = nd.x;
         const double po_sq = pomega * pomega;
         const double smx = sigma - x;
-        const double smxox = smx / x;
-        const double gg = kSqrt8Over3 * smx * sqrt(smx) / sqrt(x);
+        const double inv_x = rb_rcp(x);
+        const double smxox = smx * inv_x;
+        const double gg = kSqrt8Over3 * smx * sqrt(smx * inv_x);
 
         double y_h1, y_h2, y_f;
         if (gg < kGApproximationCutoff) {
@@ -152,8 +156,8 @@ struct HeyQRIntegrand {
         } else {
             double js, jsm1, ys, ysm1;
             bessel_jy_pair(sigma, x, js, jsm1, ys, ysm1);
-            const double jvp = jsm1 - sigma * js / x;
-            const double yvp = ysm1 - sigma * ys / x;
+            const double jvp = jsm1 - sigma * js * inv_x;
+            const double yvp = ysm1 - sigma * ys * inv_x;
             y_h1 = jvp * yvp;
             y_h2 = -js * ys;
             y_f = -x * jvp * ys;
@@ -161,7 +165,7 @@ struct HeyQRIntegrand {
 
         const double t1 = kPi * kPi * x * x * y_h1;
         const double t2 = kPi * kPi * po_sq * y_h2;
-        const double t3 = -kPi * (2.0 * po_sq + g->sigma0_sq) / sqrt(po_sq + g->sigma0_sq);
+        const double t3 = -kPi * rb_div(2.0 * po_sq + g->sigma0_sq, sqrt(po_sq + g->sigma0_sq));
         const double h = kInverseC * (t1 + t2 + t3) * nd.dfds;
         const double f = -kTwoPi * kInverseC * pomega * (kPi * y_f - 1.0) * nd.dfds;
 

@@ -74,7 +74,7 @@ RB_FN double rgamma1p(double nu)
     const int im = (int)m;
     if (im >= 0) {
         for (int i = 1; i <= im; i++)
-            r /= (mu + i);
+            r *= rb_rcp(mu + i);
     } else {
         r *= mu; // 1/Gamma(mu) = mu/Gamma(1 + mu)
     }
@@ -88,7 +88,7 @@ RB_FN_NOINLINE double bessel_j_series(double nu, double x)
     const double q = -0.25 * x * x;
     double term = 1.0, sum = 1.0;
     for (int k = 1; k < 200; k++) {
-        term *= q / (k * (k + nu));
+        term *= q * rb_rcp(k * (k + nu));
         sum += term;
         if (fabs(term) < 1e-17 * fabs(sum))
             break;
@@ -104,26 +104,29 @@ RB_FN_NOINLINE void bessel_y_temme(double mu, double x, double &y_mu, double &y_
     gamma_pair(mu, gam1, gam2, gampl, gammi);
     const double x2 = 0.5 * x;
     const double pimu = kPi * mu;
-    const double fact = (fabs(pimu) < eps) ? 1.0 : pimu / sin(pimu);
+    const double fact = (fabs(pimu) < eps) ? 1.0 : rb_div(pimu, sin(pimu));
     double d = -rb_log(x2);
     double e = mu * d;
-    const double fact2 = (fabs(e) < eps) ? 1.0 : sinh(e) / e;
+    const double fact2 = (fabs(e) < eps) ? 1.0 : rb_div(sinh(e), e);
     double ff = 2.0 / kPi * fact * (gam1 * cosh(e) + gam2 * fact2 * d);
     e = rb_exp(e);
-    double p = e / (gampl * kPi);
-    double q = 1.0 / (e * kPi * gammi);
+    double p = rb_div(e, gampl * kPi);
+    double q = rb_rcp(e * kPi * gammi);
     const double pimu2 = 0.5 * pimu;
-    const double fact3 = (fabs(pimu2) < eps) ? 1.0 : sin(pimu2) / pimu2;
+    const double fact3 = (fabs(pimu2) < eps) ? 1.0 : rb_div(sin(pimu2), pimu2);
     const double r = kPi * pimu2 * fact3 * fact3;
     double c = 1.0;
     d = -x2 * x2;
     double sum = ff + r * q;
     double sum1 = p;
     for (int i = 1; i < 500; i++) {
-        ff = (i * ff + p + q) / (i * (double)i - mu * mu);
-        c *= d / i;
-        p /= (i - mu);
-        q /= (i + mu);
+        // 1 / (i - mu), 1 / (i + mu) and 1 / (i^2 - mu^2) from one reciprocal
+        const double im = i - mu, ip = i + mu;
+        const double rr = rb_rcp(im * ip);
+        ff = (i * ff + p + q) * rr;
+        c *= d * rb_rcp((double)i);
+        p *= ip * rr;
+        q *= im * rr;
         const double del = c * (ff + r * q);
         sum += del;
         const double del1 = c * p - i * del;
@@ -132,7 +135,7 @@ RB_FN_NOINLINE void bessel_y_temme(double mu, double x, double &y_mu, double &y_
             break;
     }
     y_mu = -sum;
-    y_mu1 = -sum1 * (2.0 / x);
+    y_mu1 = -sum1 * (2.0 * rb_rcp(x));
 }
 
 // J and Y of orders sigma and sigma - 1 at x, for 0 < sigma <~ 8, 0 < x <~ 4.
@@ -153,7 +156,7 @@ RB_FN_NOINLINE void bessel_jy_pair(double sigma, double x, double &j_s, double &
         bessel_y_temme(mu, x, ya, yb); // Y_mu, Y_{mu+1}
         const int im = (int)m;
         for (int i = 1; i <= im; i++) {
-            const double yn = 2.0 * (mu + i) / x * yb - ya;
+            const double yn = 2.0 * (mu + i) * rb_rcp(x) * yb - ya;
             ya = yb;
             yb = yn;
         }
@@ -202,7 +205,7 @@ RB_FN void bessel_i_thirds(double g, double &ip13, double &im13, double &ip23, d
             break;
     }
     const double c = rb_cbrt(0.5 * g); // (g/2)^(1/3)
-    const double ci = 1.0 / c;
+    const double ci = rb_rcp(c);
     ip13 = c * 1.119846521722185685 * s0;
     im13 = ci * 0.73848811162164831294 * s1;
     ip23 = c * c * 1.1077321674324724694 * s2;

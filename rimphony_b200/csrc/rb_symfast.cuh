@@ -77,7 +77,7 @@ struct SymFastWS {
     // on the stack of the kernel, because the out-of-line quadrature functions read it through a reference
     // and the L1 left beside 214 KB of shared memory does not hold 640 stacks
     Dist dist;
-    double ctx_store[8];
+    double ctx_store[10];
 };
 
 // Warp-uniform context of one point.
@@ -86,6 +86,7 @@ struct SymFastCtx {
     const Dist *d;
     SymFastWS *ws;
     double s, cos_th, sin_th;
+    double inv_s, inv_sin_th;
     double epsrel_gamma;
 };
 
@@ -97,7 +98,7 @@ RB_FN double leung_j_below(const LeungOrder &o, double x)
 {
     if (o.kind != kOrderLeung || !(x <= o.n))
         return leung_j_general(o, x); // integer orders below 30, or x > n: out of line
-    const double eps = (o.n - x) / o.n;
+    const double eps = (o.n - x) * o.ninv;
     const bool use_debye = !(eps > o.hi_minus);
     const bool use_meissel = !(eps < o.lo_minus) && x != o.n;
     double dv = 0.0, mv = 0.0;
@@ -107,7 +108,7 @@ RB_FN double leung_j_below(const LeungOrder &o, double x)
         mv = leung_meissel_first(o, x);
     if (use_debye && use_meissel) {
         const double eta = rb_log(eps) * kLog10e;
-        const double pos = (eta - o.eta_lo_minus) / (kMinusEtaB - kMinusEtaA);
+        const double pos = (eta - o.eta_lo_minus) * (1.0 / (kMinusEtaB - kMinusEtaA));
         return dv * (1.0 - pos) + mv * pos;
     }
     return use_debye ? dv : mv;
@@ -121,8 +122,9 @@ RB_FN double sym_bessel_arg(const SymFastCtx<KIND> &cx, double n, double gamma, 
                             double &sin_xi)
 {
     const double s = cx.s, costh = cx.cos_th, sinth = cx.sin_th;
-    beta = sqrt(1.0 - 1.0 / (gamma * gamma));
-    cos_xi = (s * gamma - n) / (s * gamma * beta * costh);
+    const double inv_g = rb_rcp(gamma);
+    beta = sqrt(1.0 - inv_g * inv_g);
+    cos_xi = rb_div(s * gamma - n, s * gamma * beta * costh);
     sin_xi = sqrt(1.0 - cos_xi * cos_xi);
     double gamma_sin_xi;
     if (beta < 0.1) {
@@ -130,9 +132,10 @@ RB_FN double sym_bessel_arg(const SymFastCtx<KIND> &cx, double n, double gamma, 
     } else {
         const double bc = beta * costh;
         const double beta2_costh2 = bc * bc;
-        const double s_on_r = 2.0 * n / (s * (beta2_costh2 - 1.0));
-        const double r = 1.0 - 1.0 / beta2_costh2;
-        gamma_sin_xi = sqrt(r * (gamma * (gamma + s_on_r)) - (n * n / (s * s * beta2_costh2)));
+        const double s_on_r = 2.0 * rb_div(n, s * (beta2_costh2 - 1.0));
+        const double inv_b2c2 = rb_rcp(beta2_costh2);
+        const double nos = n * cx.inv_s;
+        gamma_sin_xi = sqrt((1.0 - inv_b2c2) * (gamma * (gamma + s_on_r)) - nos * nos * inv_b2c2);
     }
     return s * beta * sinth * gamma_sin_xi;
 }
@@ -143,17 +146,17 @@ template <int KIND>
 RB_FN_NOINLINE double sym_eps_at(const SymFastCtx<KIND> &cx, double n, double gamma)
 {
     double b_, c_, s_;
-    return (n - sym_bessel_arg<KIND>(cx, n, gamma, b_, c_, s_)) / n;
+    return rb_div(n - sym_bessel_arg<KIND>(cx, n, gamma, b_, c_, s_), n);
 }
 
 // The six gamma integrands at one node (symphony.rs:398-479); one call site.
 template <int KIND>
 RB_FN void sym_node(const SymFastCtx<KIND> &cx, double n, double gamma, double (&out)[6])
 {
-    const double costh = cx.cos_th, sinth = cx.sin_th;
+    const double costh = cx.cos_th;
     double beta, cos_xi, sin_xi;
     const double z = sym_bessel_arg<KIND>(cx, n, gamma, beta, cos_xi, sin_xi);
-    const double m = (costh - beta * cos_xi) / sinth;
+    const double m = (costh - beta * cos_xi) * cx.inv_sin_th;
     const double big_n = beta * sin_xi;
 
     // J_n(z), J_{n+1}(z): one copy of the evaluator, two trips
@@ -168,14 +171,14 @@ RB_FN void sym_node(const SymFastCtx<KIND> &cx, double n, double gamma, double (
     else if (z == 0.0)
         djn = (n >= 2.0) ? 0.0 : ((n == 0.0) ? -jv[1] : n * jn / DBL_MIN - jv[1]);
     else
-        djn = n * jn / z - jv[1];
+        djn = rb_div(n * jn, z) - jv[1];
 
     const double mj = m * jn;
     const double njp = big_n * djn;
 
     double f, dfdg, dfdcx;
     dist_eval<KIND>(*cx.d, gamma, cos_xi, f, dfdg, dfdcx);
-    const double dfdcx_factor = (beta * costh - cos_xi) / (gamma - 1.0 / gamma);
+    const double dfdcx_factor = rb_div(beta * costh - cos_xi, gamma - rb_rcp(gamma));
     const double f_abs = dfdg + dfdcx_factor * dfdcx;
 
     const double g2 = gamma * gamma;
@@ -200,11 +203,11 @@ RB_FN_NOINLINE void sym_gamma_integral(Warp &w, const SymFastCtx<KIND> &cx, doub
 {
     SymFastWS &ws = *cx.ws;
     const double s = cx.s, costh = cx.cos_th, sinth = cx.sin_th;
-    const double nos = n / s;
+    const double nos = n * cx.inv_s;
     const double root = sqrt(nos * nos - sinth * sinth);
-    const double sin2 = sinth * sinth;
-    const double gamma_minus = (nos - fabs(costh) * root) / sin2;
-    const double gamma_plus = (nos + fabs(costh) * root) / sin2;
+    const double inv_sin2 = cx.inv_sin_th * cx.inv_sin_th;
+    const double gamma_minus = (nos - fabs(costh) * root) * inv_sin2;
+    const double gamma_plus = (nos + fabs(costh) * root) * inv_sin2;
     const double gamma_peak = 0.5 * (gamma_plus + gamma_minus);
     const double rel_width = (s < 1e6) ? 1.0 : rb_exp(-0.27 * rb_log(n) - 0.1);
     // gamma = gamma_peak + t half, t in [-1, 1]
@@ -219,7 +222,7 @@ RB_FN_NOINLINE void sym_gamma_integral(Warp &w, const SymFastCtx<KIND> &cx, doub
         const double x0 = 1.0 - eps_peak;
         if (x0 > 0.0 && x0 < 1.0) {
             const double th = sqrt((1.0 - x0) * (1.0 + x0));
-            const double exponent = 2.0 * n * (rb_log((1.0 + th) / x0) - th);
+            const double exponent = 2.0 * n * (rb_log(rb_div(1.0 + th, x0)) - th);
             if (exponent > kNegligibleExponent) {
                 double *ot = ws.outer.tile;
 #ifdef RB_DEVICE_BUILD
@@ -260,7 +263,8 @@ RB_FN_NOINLINE void sym_gamma_integral(Warp &w, const SymFastCtx<KIND> &cx, doub
     PanelStack stk;
     stk.reset(&ws.inner);
     const double w_peak = rb_exp(-(1.0 / 3.0) * rb_log(n));
-    double span = kPeakSpan * w_peak / rel_width;
+    const double inv_rel_width = rb_rcp(rel_width);
+    double span = kPeakSpan * w_peak * inv_rel_width;
     const bool full = !(span < 0.5);
     if (full)
         span = 1.0;
@@ -292,7 +296,7 @@ RB_FN_NOINLINE void sym_gamma_integral(Warp &w, const SymFastCtx<KIND> &cx, doub
             const int grp = w.lane >> 3, j = w.lane & 7;
             const double tgt = (grp & 1) ? hi : lo;
             const double sg = (grp & 2) ? 1.0 : -1.0;
-            const double t0g = sqrt(2.0 * (tgt - eps0)) / rel_width; // NaN when there is no crossing
+            const double t0g = sqrt(2.0 * (tgt - eps0)) * inv_rel_width; // NaN when there is no crossing
             const double tj = t0g * (0.7 + (0.6 / 7.0) * j);
             const bool valid = leung && (eps0 < tgt) && (1.3 * t0g < span);
             double fj = 0.0;
@@ -305,7 +309,7 @@ RB_FN_NOINLINE void sym_gamma_integral(Warp &w, const SymFastCtx<KIND> &cx, doub
             const int src = 8 * grp + (ok ? cnt - 1 : 0);
             const double fa = __shfl_sync(0xffffffffu, fj, src), ta = __shfl_sync(0xffffffffu, tj, src);
             const double fb = __shfl_sync(0xffffffffu, fj, src + 1), tb = __shfl_sync(0xffffffffu, tj, src + 1);
-            const double tcross = ok ? ta - fa * (tb - ta) / (fb - fa) : NAN;
+            const double tcross = ok ? ta - fa * rb_div(tb - ta, fb - fa) : NAN;
 #pragma unroll
             for (int g = 0; g < 4; g++)
                 found[g >> 1][g & 1] = __shfl_sync(0xffffffffu, tcross, 8 * g);
@@ -313,7 +317,7 @@ RB_FN_NOINLINE void sym_gamma_integral(Warp &w, const SymFastCtx<KIND> &cx, doub
             for (int g = 0; g < 4; g++) {
                 const double tgt = (g & 1) ? hi : lo;
                 const double sg = (g & 2) ? 1.0 : -1.0;
-                const double t0g = sqrt(2.0 * (tgt - eps0)) / rel_width;
+                const double t0g = sqrt(2.0 * (tgt - eps0)) * inv_rel_width;
                 const bool valid = leung && (eps0 < tgt) && (1.3 * t0g < span);
                 double tcross = NAN;
                 if (valid) {
@@ -652,6 +656,8 @@ RB_FN void symphony_point_fast(Warp &w, const Dist &dist, double s, double theta
     cx.s = s;
     cx.cos_th = cos(theta);
     cx.sin_th = sin(theta);
+    cx.inv_s = 1.0 / s;
+    cx.inv_sin_th = 1.0 / cx.sin_th;
     cx.epsrel_gamma = epsrel_gamma;
     warp_fence();
 
