@@ -194,7 +194,7 @@ RB_FN double leung_meissel_first(const LeungOrder &o, double x)
     const double z = x / n;
     const double eps = (n - x) / n;
 #endif
-    const double Z = sqrt(eps * (1.0 + z));
+    const double Z = rb_sqrt(eps * (1.0 + z));
     const double U = rb_rcp(n * Z * Z * Z);
     const double t1 = z * z;
     const double D = kMeisselTab[0];
@@ -215,11 +215,11 @@ RB_FN double leung_meissel_first(const LeungOrder &o, double x)
     const double vsum1 = U * (p0 + U * (p1 + U * (p2 + U * (p3 + U * (p4 + U * (p5 + U * (p6 + U * p7)))))));
 
     // "I substitute Gamma(n+1) with (n+1)*Gamma(n) in the denominator" (bessel.c:123)
-    const double factor = rb_rcp((n + 1.0) * sqrt(Z));
+    const double factor = rb_rcp((n + 1.0) * rb_sqrt(Z));
 
     double exp_val;
     if (eps < 1e-4 && n > 1e3) {
-        const double exp2 = -n * sqrt(2.0 * eps) * eps *
+        const double exp2 = -n * rb_sqrt(2.0 * eps) * eps *
                             (kMeisselTab[38] + (kMeisselTab[39] + (kMeisselTab[40] + (kMeisselTab[41] + (kMeisselTab[42] +
                              (kMeisselTab[43] + kMeisselTab[44] * eps) * eps) * eps) * eps) * eps) * eps) * rb_rcp(kMeisselTab[45]);
         exp_val = o.c_stirling + exp2 - vsum1;
@@ -308,6 +308,53 @@ RB_FN double leung_debye_eps(double n, double x)
     return rb_div(lead + poly, kPi * t146 * kDebyeTab[52]);
 }
 
+// The same expansion for the orders n and n + 1 at one x (the Symphony integrand needs J_n and J_{n+1} at
+// every node): the coefficients e_0 ... e_11 and the lead term depend on x only, so they are computed once and
+// feed two Horner chains in ez = x - n and x - n - 1.  Same values as two calls of leung_debye_eps().
+RB_FN void leung_debye_eps_pair(double n0, double n1, double x, double &d0, double &d1)
+{
+    if (x > kDebyeTab[45]) {
+        d0 = d1 = NAN;
+        return;
+    }
+    const double ez0 = x - n0, ez1 = x - n1;
+    const double z = rb_cbrt(x);
+    const double t3 = z * z;
+    const double t4 = x * z;
+    const double t10 = t4 * t4;
+    const double t38 = kDebyeTab[1] * t3;
+    const double t70 = kDebyeTab[42] * t3;
+    const double t93 = kDebyeTab[43] * t3;
+    const double t107 = kDebyeTab[44] * t3;
+    const double t146 = t10 * t10;
+    const double e12a = -kDebyeTab[41] + kDebyeTab[51] * t107;
+    double p0 = e12a + kDebyeTab[8] * (ez0 * ez0), p1 = e12a + kDebyeTab[8] * (ez1 * ez1);
+#define RB_DEBYE_STEP(expr)        \
+    {                              \
+        const double ek_ = (expr); \
+        p0 = ek_ + p0 * ez0;       \
+        p1 = ek_ + p1 * ez1;       \
+    }
+    RB_DEBYE_STEP(kDebyeTab[7] * x)
+    RB_DEBYE_STEP(-kDebyeTab[50] * t107 + kDebyeTab[40])
+    RB_DEBYE_STEP((-kDebyeTab[39] + kDebyeTab[49] * t93) * x)
+    RB_DEBYE_STEP(-kDebyeTab[37] + (kDebyeTab[38] + kDebyeTab[6] * t4) * t3)
+    RB_DEBYE_STEP((kDebyeTab[36] - kDebyeTab[48] * t93) * x)
+    RB_DEBYE_STEP(kDebyeTab[33] + (-kDebyeTab[34] + (-kDebyeTab[35] + kDebyeTab[47] * t70) * t4) * t3)
+    RB_DEBYE_STEP((-kDebyeTab[31] + (kDebyeTab[32] + kDebyeTab[5] * t4) * t3) * x)
+    RB_DEBYE_STEP(-kDebyeTab[28] + (kDebyeTab[29] + (kDebyeTab[30] - kDebyeTab[46] * t70) * t4) * t3)
+    RB_DEBYE_STEP((kDebyeTab[25] + (-kDebyeTab[26] + (-kDebyeTab[27] + t38) * t4) * t3) * x)
+    RB_DEBYE_STEP(kDebyeTab[21] + (-kDebyeTab[22] + (-kDebyeTab[23] + (kDebyeTab[24] + kDebyeTab[4] * t4) * t3) * t4) * t3)
+    RB_DEBYE_STEP((-kDebyeTab[18] + (kDebyeTab[19] + (kDebyeTab[20] - t38) * t4) * t3) * x)
+    RB_DEBYE_STEP(-kDebyeTab[11] + (kDebyeTab[12] + (kDebyeTab[13] + (-kDebyeTab[14] + (kDebyeTab[15] + (-kDebyeTab[16] +
+                  (-kDebyeTab[17] + kDebyeTab[3] * t3) * t4) * t3) * z) * t3) * z) * t3)
+#undef RB_DEBYE_STEP
+    const double lead = (-kDebyeTab[9] + (kDebyeTab[10] + kDebyeTab[2] * t4) * t3) * t10 * z;
+    const double inv_den = rb_rcp(kPi * t146 * kDebyeTab[52]);
+    d0 = (lead + p0 * ez0) * inv_den;
+    d1 = (lead + p1 * ez1) * inv_den;
+}
+
 // Integer order 0 <= n < 30 (the reference calls gsl_sf_bessel_Jn,
 // bessel.c:327-334).  Miller's backward recurrence normalised by
 // J_0 + 2 sum J_2k = 1 where the recurrence is stable (x < n + 1, the only
@@ -352,6 +399,46 @@ RB_FN_NOINLINE double bessel_jn_small_int(int n, double x)
     }
     sum = 2.0 * sum + bj; // bj = J_0
     return ans / sum;
+}
+
+// J_n(x) and J_{n+1}(x) for integer 0 <= n, n + 1 < 30 and 0 < x < n + 1 from ONE backward recurrence (the
+// Symphony integrand needs both at every node, and the recurrence is the whole cost of a discrete harmonic).
+RB_FN_NOINLINE void bessel_jn_pair_small_int(int n, double x, double &jn, double &jn1)
+{
+    const double tox = 2.0 * rb_rcp(x);
+    int k = 2 * ((n + 47) / 2);
+    double kd = (double)k;
+    double bjp = 0.0, bj = 1.0, sum = 0.0, a0 = 0.0, a1 = 0.0;
+    // state at the top of a step: bj = J_k, bjp = J_{k+1} (unnormalised); a step goes from k to k - 1.
+    // Two loops with the same body: down to k = n + 1, where J_{n+1} and then J_n are taken, and on to k = 0.
+#pragma unroll 1
+    for (int phase = 0; phase < 2; phase++) {
+        const int k_end = phase ? 0 : n + 1;
+#pragma unroll 1
+        while (k > k_end) {
+            const double bjm = kd * tox * bj - bjp;
+            bjp = bj;
+            bj = bjm;
+            kd -= 1.0;
+            k--;
+            if (fabs(bj) > 1e150) {
+                bj *= 1e-150;
+                bjp *= 1e-150;
+                a0 *= 1e-150;
+                a1 *= 1e-150;
+                sum *= 1e-150;
+            }
+            if ((k & 1) == 0 && k > 0)
+                sum += bj;
+            if (k == n)
+                a0 = bj; // (taken in the first step of the second phase)
+        }
+        if (phase == 0)
+            a1 = bj;
+    }
+    const double inv = rb_rcp(2.0 * sum + bj); // bj = J_0
+    jn = a0 * inv;
+    jn1 = a1 * inv;
 }
 
 // pkgw_bessel_j (bessel.c:318-376).

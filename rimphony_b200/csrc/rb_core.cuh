@@ -64,47 +64,7 @@ namespace rb {
 // cubic Newton step (6 instructions, <= 1.5 ulp; b = 0, |b| < 2^-1022, |b| = inf give NaN, |b| > 2^1022 gives
 // 0: no node of a quadrature rule depends on those), exp and log with their coefficients read from the
 // constant bank as instruction operands (32 / 38 instructions, <= 2 ulp).
-#if defined(RB_LEAN_MATH)
-#ifdef RB_DEVICE_BUILD
-RB_FN double rb_rcp_seed(double b)
-{
-    double r;
-    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(b));
-    return r;
-}
-#else
-// what MUFU.RCP64H returns, to 2^-23: subnormal arguments and results are flushed to zero
-inline double rb_rcp_seed(double b)
-{
-    if (b != b)
-        return b;
-    const double ab = fabs(b);
-    if (ab < DBL_MIN)
-        return copysign(INFINITY, b);
-    if (ab > 0x1p1022)
-        return copysign(0.0, b);
-    return (1.0 / b) * (1.0 + 0x1p-24);
-}
-#endif
-RB_FN double rb_rcp(double b)
-{
-    const double r = rb_rcp_seed(b);
-    double e = fma(-b, r, 1.0);
-    e = fma(e, e, e);
-    return fma(r, e, r);
-}
-RB_FN double rb_div(double a, double b) { return a * rb_rcp(b); }
-
-// exp(r) on |r| <= ln(2)/2: Taylor to r^13 (remainder 4e-18), highest power first
-RB_TABLE double EXP_POLY[14] = {1.0 / 6227020800.0, 1.0 / 479001600.0, 1.0 / 39916800.0, 1.0 / 3628800.0, 1.0 / 362880.0,
-                                1.0 / 40320.0,      1.0 / 5040.0,      1.0 / 720.0,      1.0 / 120.0,     1.0 / 24.0,
-                                1.0 / 6.0,          0.5,               1.0,              1.0};
-// log2(e), -ln(2) in two parts: read from the table like the coefficients (a literal costs two UMOVs)
-RB_TABLE double LN2_CONST[3] = {1.4426950408889634074, -6.93147180559945286227e-01, -2.31904681384629955842e-17};
-// log(m) = 2 atanh(f), f = (m - 1) / (m + 1), |f| <= 0.1716: 2 f + f^3 (2/3 + 2/5 f^2 + ... + 2/23 f^20)
-RB_TABLE double LOG_POLY[11] = {2.0 / 23.0, 2.0 / 21.0, 2.0 / 19.0, 2.0 / 17.0, 2.0 / 15.0, 2.0 / 13.0,
-                                2.0 / 11.0, 2.0 / 9.0,  2.0 / 7.0,  2.0 / 5.0,  2.0 / 3.0};
-
+// the two words of a double
 RB_FN int rb_hi32(double x)
 {
 #ifdef RB_DEVICE_BUILD
@@ -136,6 +96,84 @@ RB_FN double rb_from_hilo(int hi, int lo)
     return x;
 #endif
 }
+
+#if defined(RB_LEAN_MATH)
+#ifdef RB_DEVICE_BUILD
+RB_FN double rb_rcp_seed(double b)
+{
+    double r;
+    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(b));
+    return r;
+}
+#else
+// what MUFU.RCP64H returns, to 2^-23: subnormal arguments and results are flushed to zero
+inline double rb_rcp_seed(double b)
+{
+    if (b != b)
+        return b;
+    const double ab = fabs(b);
+    if (ab < DBL_MIN)
+        return copysign(INFINITY, b);
+    if (ab > 0x1p1022)
+        return copysign(0.0, b);
+    return (1.0 / b) * (1.0 + 0x1p-24);
+}
+#endif
+RB_FN double rb_rcp(double b)
+{
+    const double r = rb_rcp_seed(b);
+    double e = fma(-b, r, 1.0);
+    e = fma(e, e, e);
+    return fma(r, e, r);
+}
+RB_FN double rb_div(double a, double b) { return a * rb_rcp(b); }
+
+// Square root from MUFU.RSQ64H (2^-22) and two coupled Newton steps on (sqrt x, 1 / (2 sqrt x)): 11 instructions
+// where the IEEE-correct sequence with its range check takes 19; <= 1 ulp.  +-0 and subnormal arguments give 0,
+// negative ones NaN; +inf gives NaN (no caller can tell: an infinite node value ends in NaN either way).
+#ifdef RB_DEVICE_BUILD
+RB_FN double rb_rsqrt_seed(double x)
+{
+    double y;
+    asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(x));
+    return y;
+}
+#else
+inline double rb_rsqrt_seed(double x)
+{
+    if (x != x || x < 0.0)
+        return NAN;
+    if (x < DBL_MIN)
+        return INFINITY;
+    if (x == INFINITY)
+        return 0.0;
+    return (1.0 / sqrt(x)) * (1.0 + 0x1p-23);
+}
+#endif
+RB_FN double rb_sqrt(double x)
+{
+#ifdef RB_NO_LEAN_SQRT
+    return sqrt(x);
+#endif
+    const double y = rb_rsqrt_seed(x);
+    double g = x * y, h = 0.5 * y;
+    const double r = fma(-h, g, 0.5);
+    g = fma(g, r, g);
+    h = fma(h, r, h);
+    const double d = fma(-g, g, x);
+    g = fma(d, h, g);
+    return (fabs(x) < DBL_MIN) ? 0.0 : g;
+}
+
+// exp(r) on |r| <= ln(2)/2: Taylor to r^13 (remainder 4e-18), highest power first
+RB_TABLE double EXP_POLY[14] = {1.0 / 6227020800.0, 1.0 / 479001600.0, 1.0 / 39916800.0, 1.0 / 3628800.0, 1.0 / 362880.0,
+                                1.0 / 40320.0,      1.0 / 5040.0,      1.0 / 720.0,      1.0 / 120.0,     1.0 / 24.0,
+                                1.0 / 6.0,          0.5,               1.0,              1.0};
+// log2(e), -ln(2) in two parts: read from the table like the coefficients (a literal costs two UMOVs)
+RB_TABLE double LN2_CONST[3] = {1.4426950408889634074, -6.93147180559945286227e-01, -2.31904681384629955842e-17};
+// log(m) = 2 atanh(f), f = (m - 1) / (m + 1), |f| <= 0.1716: 2 f + f^3 (2/3 + 2/5 f^2 + ... + 2/23 f^20)
+RB_TABLE double LOG_POLY[11] = {2.0 / 23.0, 2.0 / 21.0, 2.0 / 19.0, 2.0 / 17.0, 2.0 / 15.0, 2.0 / 13.0,
+                                2.0 / 11.0, 2.0 / 9.0,  2.0 / 7.0,  2.0 / 5.0,  2.0 / 3.0};
 
 #ifdef RB_DEVICE_BUILD
 static __device__ __noinline__
@@ -199,6 +237,7 @@ inline double rb_cbrt(double x) { return cbrt(x); }
 #else // !RB_LEAN_MATH
 RB_FN double rb_rcp(double b) { return 1.0 / b; }
 RB_FN double rb_div(double a, double b) { return a / b; }
+RB_FN double rb_sqrt(double x) { return sqrt(x); }
 #if defined(RB_DEVICE_BUILD) && !defined(RB_INLINE_MATH) // measured: +9 % sets/s over inlining
 static __device__ __noinline__ double rb_log(double x) { return log(x); }
 static __device__ __noinline__ double rb_exp(double x) { return exp(x); }

@@ -93,8 +93,8 @@ RB_FN void dist_eval(const Dist &d, double gamma, double cos_xi, double &f, doub
             return;
         }
         const double g2m1 = gamma * gamma - 1.0;
-        // norm gamma^-p rb_exp(-gamma/gc) / (gamma^2 beta),  gamma^2 beta = gamma sqrt(gamma^2 - 1)
-        const double sq = sqrt(g2m1);
+        // norm gamma^-p rb_exp(-gamma/gc) / (gamma^2 beta),  gamma^2 beta = gamma rb_sqrt(gamma^2 - 1)
+        const double sq = rb_sqrt(g2m1);
         const double inv = rb_rcp(gamma * sq); // 1 / (gamma^2 beta); 1 / gamma = inv sq, 1 / (gamma^2 - 1) = (inv gamma)^2
         const double ig = inv * gamma;
         f = d.norm * rb_exp(-d.p * rb_log(gamma) - gamma * d.inv_gamma_cutoff) * inv;
@@ -111,7 +111,7 @@ RB_FN void dist_eval(const Dist &d, double gamma, double cos_xi, double &f, doub
         }
         const double sin2 = (sin2_exact == sin2_exact) ? sin2_exact : 1.0 - cos_xi * cos_xi;
         const double g2m1 = gamma * gamma - 1.0;
-        const double sq = sqrt(g2m1);
+        const double sq = rb_sqrt(g2m1);
         const double inv = rb_rcp(gamma * sq); // 1 / (gamma^2 beta); 1 / gamma = inv sq, 1 / (gamma^2 - 1) = (inv gamma)^2
         const double ig = inv * gamma;
         f = d.norm * rb_exp(log_pitch_term(d.k, sin2) - d.p * rb_log(gamma) - gamma * d.inv_gamma_cutoff) * inv;

@@ -276,7 +276,7 @@ RB_FN double quad_error(double d, double a, double hl)
     double err = fabs(d * hl);
     if (rabs != 0.0 && err != 0.0) {
         const double qq = 200.0 * rb_div(err, rabs);
-        const double scale = qq * sqrt(qq);
+        const double scale = qq * rb_sqrt(qq);
         err = (scale < 1.0) ? rabs * scale : rabs;
     }
     const double min_err = 50.0 * DBL_EPSILON * rabs;
@@ -402,7 +402,7 @@ RB_FN_NOINLINE void tile_reduce(const double *tile, int nv, double hl, PerChan<d
         double err = fabs(d * hl);
         if (rabs != 0.0 && err != 0.0) {
             const double qq = 200.0 * rb_div(err, rabs);
-            const double scale = qq * sqrt(qq);
+            const double scale = qq * rb_sqrt(qq);
             err = (scale < 1.0) ? rabs * scale : rabs;
         }
         const double min_err = 50.0 * DBL_EPSILON * rabs;

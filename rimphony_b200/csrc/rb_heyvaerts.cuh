@@ -45,11 +45,11 @@ struct HeyNode {
     {
         sigma = sigma_;
         pomega = pomega_;
-        x = (x_exact == x_exact) ? x_exact : sqrt(sigma * sigma - pomega * pomega - g.sigma0_sq);
+        x = (x_exact == x_exact) ? x_exact : rb_sqrt(sigma * sigma - pomega * pomega - g.sigma0_sq);
         const double t = g.sigma0 * g.sin_th;
         const double inv_t = rb_rcp(t);
         const double gamma = (sigma - pomega * g.cos_th) * inv_t;
-        double mu = rb_div(sigma * g.cos_th - pomega, t * sqrt(gamma * gamma - 1.0));
+        double mu = rb_div(sigma * g.cos_th - pomega, t * rb_sqrt(gamma * gamma - 1.0));
 
         // sin^2(xi) = 1 - mu^2 = x^2 sin^2(theta) / ((sigma - pomega cos(theta))^2 - t^2) identically.
         // Where the caller knows x without cancellation (the product path's substitutions) this
@@ -63,7 +63,7 @@ struct HeyNode {
             const double xs = x * g.sin_th;
             sin2 = rb_div(xs * xs, (q - t) * (q + t));
             if (sin2 <= 1.0) {
-                const double mag = sqrt(1.0 - sin2);
+                const double mag = rb_sqrt(1.0 - sin2);
                 if (fabs(mu) > mag || !(mu == mu))
                     mu = (sigma * g.cos_th - pomega < 0.0) ? -mag : mag;
             } else
@@ -79,7 +79,7 @@ struct HeyNode {
             const double q = sigma - pomega * g.cos_th;
             const double r = pomega - sigma * g.cos_th;
             const double u = q * q - t * t;
-            const double dcxi_dsigma = rb_div(q * u * g.cos_th + u * r + r * t * t, u * sqrt(u) * q);
+            const double dcxi_dsigma = rb_div(q * u * g.cos_th + u * r + r * t * t, u * rb_sqrt(u) * q);
             mu_term = dcxi_dsigma * dfdcxi;
         }
         dfds = g_term + mu_term;
@@ -101,8 +101,8 @@ struct HeyNRIntegrand {
         const double s_sq = sigma * sigma;
         const double x_sq = nd.x * nd.x;
         const double v = s_sq - x_sq;
-        const double sv = sqrt(v);
-        // powers of 1 / sqrt(v) from one reciprocal (the reference divides seven times, heyvaerts.rs:379-394)
+        const double sv = rb_sqrt(v);
+        // powers of 1 / rb_sqrt(v) from one reciprocal (the reference divides seven times, heyvaerts.rs:379-394)
         const double isv = rb_rcp(sv);
         const double iv = isv * isv, iv15 = iv * isv, iv2 = iv * iv, iv25 = iv2 * isv;
         const double ratio = s_sq * iv;
@@ -144,7 +144,7 @@ struct HeyQRIntegrand {
         const double smx = sigma - x;
         const double inv_x = rb_rcp(x);
         const double smxox = smx * inv_x;
-        const double gg = kSqrt8Over3 * smx * sqrt(smx * inv_x);
+        const double gg = kSqrt8Over3 * smx * rb_sqrt(smx * inv_x);
 
         double y_h1, y_h2, y_f;
         if (gg < kGApproximationCutoff) {
@@ -165,7 +165,7 @@ struct HeyQRIntegrand {
 
         const double t1 = kPi * kPi * x * x * y_h1;
         const double t2 = kPi * kPi * po_sq * y_h2;
-        const double t3 = -kPi * rb_div(2.0 * po_sq + g->sigma0_sq, sqrt(po_sq + g->sigma0_sq));
+        const double t3 = -kPi * rb_div(2.0 * po_sq + g->sigma0_sq, rb_sqrt(po_sq + g->sigma0_sq));
         const double h = kInverseC * (t1 + t2 + t3) * nd.dfds;
         const double f = -kTwoPi * kInverseC * pomega * (kPi * y_f - 1.0) * nd.dfds;
 

@@ -94,24 +94,33 @@ struct SymFastCtx {
 // Debye and Meissel expansions appear once each (pkgw_bessel_j, bessel.c:318-357).
 RB_FN_NOINLINE double leung_j_general(const LeungOrder &o, double x) { return leung_j(o, x); }
 
-RB_FN double leung_j_below(const LeungOrder &o, double x)
+// J_n(x) and J_{n+1}(x), n >= 30, 0 <= x <= n (pkgw_bessel_j, bessel.c:341-357, for both orders), with the
+// Debye expansion evaluated once for both (leung_debye_eps_pair).
+RB_FN void leung_j_pair_below(const LeungOrder &o0, const LeungOrder &o1, double x, double (&jv)[2])
 {
-    if (o.kind != kOrderLeung || !(x <= o.n))
-        return leung_j_general(o, x); // integer orders below 30, or x > n: out of line
-    const double eps = (o.n - x) * o.ninv;
-    const bool use_debye = !(eps > o.hi_minus);
-    const bool use_meissel = !(eps < o.lo_minus) && x != o.n;
-    double dv = 0.0, mv = 0.0;
-    if (use_debye)
-        dv = leung_debye_eps(o.n, x);
-    if (use_meissel)
-        mv = leung_meissel_first(o, x);
-    if (use_debye && use_meissel) {
-        const double eta = rb_log(eps) * kLog10e;
-        const double pos = (eta - o.eta_lo_minus) * (1.0 / (kMinusEtaB - kMinusEtaA));
-        return dv * (1.0 - pos) + mv * pos;
+    const double eps0 = (o0.n - x) * o0.ninv, eps1 = (o1.n - x) * o1.ninv;
+    const bool deb0 = !(eps0 > o0.hi_minus), deb1 = !(eps1 > o1.hi_minus);
+    const bool mei0 = !(eps0 < o0.lo_minus) && x != o0.n, mei1 = !(eps1 < o1.lo_minus);
+    double dv[2] = {0.0, 0.0};
+    if (deb0 || deb1)
+        leung_debye_eps_pair(o0.n, o1.n, x, dv[0], dv[1]);
+#pragma unroll 1
+    for (int k = 0; k < 2; k++) {
+        const LeungOrder &o = k ? o1 : o0;
+        const double eps = k ? eps1 : eps0;
+        const bool use_debye = k ? deb1 : deb0, use_meissel = k ? mei1 : mei0;
+        double v = dv[k];
+        if (use_meissel) {
+            const double mv = leung_meissel_first(o, x);
+            v = mv;
+            if (use_debye) {
+                const double eta = rb_log(eps) * kLog10e;
+                const double pos = (eta - o.eta_lo_minus) * (1.0 / (kMinusEtaB - kMinusEtaA));
+                v = dv[k] * (1.0 - pos) + mv * pos;
+            }
+        }
+        jv[k] = v;
     }
-    return use_debye ? dv : mv;
 }
 
 // Kinematics of one (n, gamma) node: beta, cos/sin of the pitch angle xi fixed by the
@@ -123,9 +132,9 @@ RB_FN double sym_bessel_arg(const SymFastCtx<KIND> &cx, double n, double gamma, 
 {
     const double s = cx.s, costh = cx.cos_th, sinth = cx.sin_th;
     const double inv_g = rb_rcp(gamma);
-    beta = sqrt(1.0 - inv_g * inv_g);
+    beta = rb_sqrt(1.0 - inv_g * inv_g);
     cos_xi = rb_div(s * gamma - n, s * gamma * beta * costh);
-    sin_xi = sqrt(1.0 - cos_xi * cos_xi);
+    sin_xi = rb_sqrt(1.0 - cos_xi * cos_xi);
     double gamma_sin_xi;
     if (beta < 0.1) {
         gamma_sin_xi = gamma * sin_xi;
@@ -135,7 +144,7 @@ RB_FN double sym_bessel_arg(const SymFastCtx<KIND> &cx, double n, double gamma, 
         const double s_on_r = 2.0 * rb_div(n, s * (beta2_costh2 - 1.0));
         const double inv_b2c2 = rb_rcp(beta2_costh2);
         const double nos = n * cx.inv_s;
-        gamma_sin_xi = sqrt((1.0 - inv_b2c2) * (gamma * (gamma + s_on_r)) - nos * nos * inv_b2c2);
+        gamma_sin_xi = rb_sqrt((1.0 - inv_b2c2) * (gamma * (gamma + s_on_r)) - nos * nos * inv_b2c2);
     }
     return s * beta * sinth * gamma_sin_xi;
 }
@@ -161,9 +170,15 @@ RB_FN void sym_node(const SymFastCtx<KIND> &cx, double n, double gamma, double (
 
     // J_n(z), J_{n+1}(z): one copy of the evaluator, two trips
     double jv[2];
+    if (cx.ws->on1.kind == kOrderInteger && cx.ws->on.kind == kOrderInteger && z > 0.0 && z < n + 1.0) {
+        bessel_jn_pair_small_int(cx.ws->on.nint, z, jv[0], jv[1]); // a discrete harmonic below order 29
+    } else if (cx.ws->on.kind == kOrderLeung && cx.ws->on1.kind == kOrderLeung && z <= n) {
+        leung_j_pair_below(cx.ws->on, cx.ws->on1, z, jv);
+    } else { // order 29 with 30, the first harmonics of s sin(theta) < 1: out of line
 #pragma unroll 1
-    for (int k = 0; k < 2; k++)
-        jv[k] = leung_j_below(k ? cx.ws->on1 : cx.ws->on, z);
+        for (int k = 0; k < 2; k++)
+            jv[k] = leung_j_general(k ? cx.ws->on1 : cx.ws->on, z);
+    }
     const double jn = jv[0];
     double djn;
     if (n >= 1e15)
