@@ -98,13 +98,16 @@ RB_FN unsigned lockstep_tick(bool idle = false)
 RB_FN unsigned lockstep_tick(bool = false) { return 0; }
 #endif
 
-// per-warp shared-memory working set of one quadrature level
-struct EngLevel {
-    double tile[kEngTile];
+// per-warp shared-memory working set of one quadrature level; CH = channel rows of the tile (the Heyvaerts
+// kernel has two integrands: a quarter of the shared memory, which is what bounds its CTAs per SM)
+template <int CH>
+struct EngLevelT {
+    double tile[2 * CH * kEngRow];
     double stk_a[kEngStack];
     double stk_b[kEngStack];
     int stk_tag[kEngStack];
 };
+using EngLevel = EngLevelT<kEngChan>;
 
 // Per-channel state: one register on the device (the lane's own channel), an
 // array in the host emulation.
@@ -202,7 +205,7 @@ RB_TABLE double GK7_WD[7] = {0.1046562260264672651938239, 0.26848808986833344072
 RB_FN int tile_col(int node) { return node + (node >> 3); }
 
 // Store the node values of one lane (node = lane) into a tile, pre-weighted.
-template <int NV>
+template <int NV, int CH = kEngChan>
 RB_FN void tile_store(double *tile, const Warp &w, int node, const double (&vals)[NV])
 {
 #ifdef RB_DEVICE_BUILD
@@ -218,7 +221,7 @@ RB_FN void tile_store(double *tile, const Warp &w, int node, const double (&vals
     for (int c = 0; c < NV; c++) {
         const double f = (node < 31) ? vals[c] : 0.0;
         tile[c * kEngRow + col] = wk * f;
-        tile[(kEngChan + c) * kEngRow + col] = wd * f;
+        tile[(CH + c) * kEngRow + col] = wd * f;
     }
 }
 
@@ -258,7 +261,7 @@ RB_LANE_TABLE double L15_WK[32] = {RB_K15_ROW(RB_K15WK), RB_K15_ROW(RB_K15WK)};
 RB_LANE_TABLE double L15_WD[32] = {RB_K15_ROW(RB_K15WD), RB_K15_ROW(RB_K15WD)};
 
 // Store the node values of lane `lane` with explicit weights (multi-panel layouts).
-template <int NV>
+template <int NV, int CH = kEngChan>
 RB_FN void tile_store_weighted(double *tile, int lane, double wk, double wd, const double (&vals)[NV])
 {
     const int col = tile_col(lane);
@@ -266,7 +269,7 @@ RB_FN void tile_store_weighted(double *tile, int lane, double wk, double wd, con
     for (int c = 0; c < NV; c++) {
         const double f = (wk != 0.0) ? vals[c] : 0.0;
         tile[c * kEngRow + col] = wk * f;
-        tile[(kEngChan + c) * kEngRow + col] = wd * f;
+        tile[(CH + c) * kEngRow + col] = wd * f;
     }
 }
 
@@ -285,6 +288,7 @@ RB_FN double quad_error(double d, double a, double hl)
 
 // Reduce a tile that holds two 15-point panels (columns of quarters 0-1 and 2-3) of half-lengths
 // hl0, hl1: per channel the estimates (r0, e0) and (r1, e1) of the two panels.
+template <int CH = kEngChan>
 RB_FN_NOINLINE void tile_reduce_pair(const double *tile, int nv, double hl0, double hl1, PerChan<double> &r0,
                                      PerChan<double> &e0, PerChan<double> &r1, PerChan<double> &e1)
 {
@@ -294,7 +298,7 @@ RB_FN_NOINLINE void tile_reduce_pair(const double *tile, int nv, double hl0, dou
     double k = 0.0, d = 0.0, a = 0.0;
     if (c < nv) {
         const double *ra = tile + c * kEngRow + 9 * q;
-        const double *rb = ra + kEngChan * kEngRow;
+        const double *rb = ra + CH * kEngRow;
 #pragma unroll
         for (int t = 0; t < 8; t++) {
             const double va = ra[t];
@@ -326,7 +330,7 @@ RB_FN_NOINLINE void tile_reduce_pair(const double *tile, int nv, double hl0, dou
                     const double va = tile[c * kEngRow + 9 * q + t];
                     kq += va;
                     aq += fabs(va);
-                    dq += tile[(kEngChan + c) * kEngRow + 9 * q + t];
+                    dq += tile[(CH + c) * kEngRow + 9 * q + t];
                 }
                 k += kq;
                 d += dq;
@@ -340,14 +344,15 @@ RB_FN_NOINLINE void tile_reduce_pair(const double *tile, int nv, double hl0, dou
 #endif
 }
 
+template <int CH = kEngChan>
 RB_FN void tile_clear(const Warp &w, double *tile)
 {
 #ifdef RB_DEVICE_BUILD
-    for (int i = w.lane; i < kEngTile; i += 32)
+    for (int i = w.lane; i < 2 * CH * kEngRow; i += 32)
         tile[i] = 0.0;
 #else
     (void)w;
-    for (int i = 0; i < kEngTile; i++)
+    for (int i = 0; i < 2 * CH * kEngRow; i++)
         tile[i] = 0.0;
 #endif
 }
@@ -357,6 +362,7 @@ RB_FN void tile_clear(const Warp &w, double *tile)
 // (200 |K - G| / scale)^1.5 heuristic with the integral of |f| as the scale (the
 // reference's second pass for the integral of |f - mean| is not needed at the
 // tolerances of this path), floored at 50 ulp of the integral of |f|.
+template <int CH = kEngChan>
 RB_FN_NOINLINE void tile_reduce(const double *tile, int nv, double hl, PerChan<double> &r, PerChan<double> &e)
 {
 #ifdef RB_DEVICE_BUILD
@@ -365,7 +371,7 @@ RB_FN_NOINLINE void tile_reduce(const double *tile, int nv, double hl, PerChan<d
     double k = 0.0, d = 0.0, a = 0.0;
     if (c < nv) {
         const double *ra = tile + c * kEngRow + 9 * q;
-        const double *rb = ra + kEngChan * kEngRow;
+        const double *rb = ra + CH * kEngRow;
 #pragma unroll
         for (int t = 0; t < 8; t++) {
             const double va = ra[t];
@@ -390,7 +396,7 @@ RB_FN_NOINLINE void tile_reduce(const double *tile, int nv, double hl, PerChan<d
                 const double va = tile[c * kEngRow + 9 * q + t];
                 kq += va;
                 aq += fabs(va);
-                dq += tile[(kEngChan + c) * kEngRow + 9 * q + t];
+                dq += tile[(CH + c) * kEngRow + 9 * q + t];
             }
             k += kq;
             d += dq;
@@ -429,12 +435,18 @@ RB_FN bool chan_all(const PerChan<bool> &ok, int nv)
 
 // A pending-panel stack (warp-uniform; lane 0 writes, everybody reads).
 struct PanelStack {
-    EngLevel *lv;
+    struct Arrays {
+        double *stk_a, *stk_b;
+        int *stk_tag;
+    } store;
     int sp;
 
-    RB_FN void reset(EngLevel *level)
+    template <int CH>
+    RB_FN void reset(EngLevelT<CH> *level)
     {
-        lv = level;
+        store.stk_a = level->stk_a;
+        store.stk_b = level->stk_b;
+        store.stk_tag = level->stk_tag;
         sp = 0;
         warp_fence();
     }
@@ -445,9 +457,9 @@ struct PanelStack {
         if (w.lane == 0)
 #endif
         {
-            lv->stk_a[sp] = a;
-            lv->stk_b[sp] = b;
-            lv->stk_tag[sp] = tag;
+            store.stk_a[sp] = a;
+            store.stk_b[sp] = b;
+            store.stk_tag[sp] = tag;
         }
         sp++;
     }
@@ -461,14 +473,14 @@ struct PanelStack {
 #endif
         {
             for (int i = 0, j = sp - 1; i < j; i++, j--) {
-                const double a = lv->stk_a[i], b = lv->stk_b[i];
-                const int g = lv->stk_tag[i];
-                lv->stk_a[i] = lv->stk_a[j];
-                lv->stk_b[i] = lv->stk_b[j];
-                lv->stk_tag[i] = lv->stk_tag[j];
-                lv->stk_a[j] = a;
-                lv->stk_b[j] = b;
-                lv->stk_tag[j] = g;
+                const double a = store.stk_a[i], b = store.stk_b[i];
+                const int g = store.stk_tag[i];
+                store.stk_a[i] = store.stk_a[j];
+                store.stk_b[i] = store.stk_b[j];
+                store.stk_tag[i] = store.stk_tag[j];
+                store.stk_a[j] = a;
+                store.stk_b[j] = b;
+                store.stk_tag[j] = g;
             }
         }
         warp_fence();
@@ -476,9 +488,9 @@ struct PanelStack {
     RB_FN void pop(double &a, double &b, int &tag)
     {
         sp--;
-        a = lv->stk_a[sp];
-        b = lv->stk_b[sp];
-        tag = lv->stk_tag[sp];
+        a = store.stk_a[sp];
+        b = store.stk_b[sp];
+        tag = store.stk_tag[sp];
     }
 };
 

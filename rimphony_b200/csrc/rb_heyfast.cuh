@@ -27,6 +27,7 @@
 
 namespace rb {
 
+constexpr int kHeyChan = 2; // channel rows of the tiles: rho_Q and rho_V
 constexpr double kHeyInnerFloor = 1.0;
 constexpr double kHeyInnerWidth = 4.0; // widest NR inner seed panel in t = arccosh(sigma / sigma_min)
 constexpr double kHeyPanelWidth = 2.0; // widest outer panel in the log of the variable
@@ -79,7 +80,7 @@ RB_HD double hey_ref_diverges_q(bool isotropic, double sin_th, double cos_th)
 }
 
 struct HeyFastWS {
-    EngLevel inner, outer;
+    EngLevelT<kHeyChan> inner, outer;
     // the warp-uniform context of the point in work, in shared memory rather than on the kernel's stack
     // (see SymFastWS)
     Dist dist;
@@ -257,7 +258,7 @@ RB_FN_NOINLINE bool hey_inner_integral(Warp &w, const HeyFastCtx<KIND> &cx, int 
                 } else
                     f.eval(t, vals);
             }
-            tile_store<2>(ws.inner.tile, w, w.lane, vals);
+            tile_store<2, kHeyChan>(ws.inner.tile, w, w.lane, vals);
         }
 #else
         for (int l = 0; l < 32; l++) {
@@ -283,14 +284,14 @@ RB_FN_NOINLINE bool hey_inner_integral(Warp &w, const HeyFastCtx<KIND> &cx, int 
                 } else
                     f.eval(t, vals);
             }
-            tile_store<2>(ws.inner.tile, w, l, vals);
+            tile_store<2, kHeyChan>(ws.inner.tile, w, l, vals);
         }
 #endif
         w.n_apply_lanes++;
         warp_fence();
 
         PerChan<double> r, e;
-        tile_reduce(ws.inner.tile, 2, thl, r, e);
+        tile_reduce<kHeyChan>(ws.inner.tile, 2, thl, r, e);
 
         PerChan<bool> ok;
         RB_FOR_CHAN(c, kEngChan) { ok[c] = true; }
@@ -335,7 +336,7 @@ RB_FN_NOINLINE bool hey_inner_integral(Warp &w, const HeyFastCtx<KIND> &cx, int 
         RB_FOR_CHAN(c, 2)
         {
             ot[c * kEngRow + col] = wa * sum[c];
-            ot[(kEngChan + c) * kEngRow + col] = wb * sum[c];
+            ot[(kHeyChan + c) * kEngRow + col] = wb * sum[c];
         }
     }
     return all_nan;
@@ -398,7 +399,7 @@ RB_FN_NOINLINE void hey_outer_integral(Warp &w, const HeyFastCtx<KIND> &cx, int 
         big[c] = 0.0;
     }
     warp_fence();
-    tile_clear(w, ws.outer.tile);
+    tile_clear<kHeyChan>(w, ws.outer.tile);
     int filled = 0;
 
     while (stk.sp > 0) {
@@ -420,7 +421,7 @@ RB_FN_NOINLINE void hey_outer_integral(Warp &w, const HeyFastCtx<KIND> &cx, int 
         const double *rwk = narrow ? GK7_WK : GK15_WK;
         const double *rwd = narrow ? GK7_WD : GK15_WD;
         if (n_nodes < filled) {
-            tile_clear(w, ws.outer.tile);
+            tile_clear<kHeyChan>(w, ws.outer.tile);
             warp_fence();
         }
         filled = n_nodes;
@@ -443,7 +444,7 @@ RB_FN_NOINLINE void hey_outer_integral(Warp &w, const HeyFastCtx<KIND> &cx, int 
         }
         warp_fence();
         PerChan<double> r, e;
-        tile_reduce(ws.outer.tile, 2, thl, r, e);
+        tile_reduce<kHeyChan>(ws.outer.tile, 2, thl, r, e);
 
         PerChan<bool> ok;
         RB_FOR_CHAN(c, kEngChan) { ok[c] = true; }
@@ -490,14 +491,14 @@ RB_FN void hey_outer_derivative(Warp &w, const HeyFastCtx<KIND> &cx, int which, 
 {
     HeyFastWS &ws = *cx.ws;
     warp_fence();
-    tile_clear(w, ws.outer.tile);
+    tile_clear<kHeyChan>(w, ws.outer.tile);
     warp_fence();
     const double dv = kHeyDerivStep * fabs(v);
     hey_inner_integral<KIND>(w, cx, which, v - dv, tile_col(0), -0.5 / dv, 0.0);
     hey_inner_integral<KIND>(w, cx, which, v + dv, tile_col(1), 0.5 / dv, 0.0);
     warp_fence();
     PerChan<double> unused;
-    tile_reduce(ws.outer.tile, 2, 1.0, deriv, unused);
+    tile_reduce<kHeyChan>(ws.outer.tile, 2, 1.0, deriv, unused);
 }
 
 // One outward-stepping stage of heyvaerts.rs:102-185 (cf. hey_step_outward<> in

@@ -137,6 +137,9 @@ __global__ void __launch_bounds__(kThreadsPerBlock, 4) k_symphony_diag(BatchArgs
 #ifndef RB_FAST_BLOCKS
 #define RB_FAST_BLOCKS 5 // resident CTAs per SM the product kernels are compiled for (96 registers; +5 % over 4)
 #endif
+#ifndef RB_HEY_BLOCKS
+#define RB_HEY_BLOCKS 10 // the Heyvaerts kernel (48 registers; its tiles have two channel rows, 14 KB per CTA): 5 -> 10 CTAs per SM is -13 % kernel time, 12 and 16 are slower again
+#endif
 #ifndef RB_FAST_WARPS
 #define RB_FAST_WARPS 4 // warps per CTA of the product kernels
 #endif
@@ -287,7 +290,7 @@ __global__ void __launch_bounds__(kThreadsPerBlock, 4) k_heyvaerts(BatchArgs a)
 
 // The product path for rho_Q, rho_V: compact engine (rb_engine.cuh, rb_heyfast.cuh).
 template <int KIND>
-__global__ void __launch_bounds__(kFastThreads, RB_FAST_BLOCKS) k_heyvaerts_fast(BatchArgs a)
+__global__ void __launch_bounds__(kFastThreads, RB_HEY_BLOCKS) k_heyvaerts_fast(BatchArgs a)
 {
     extern __shared__ double smem[];
     lockstep_init();

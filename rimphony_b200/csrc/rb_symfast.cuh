@@ -69,8 +69,10 @@ constexpr double kNarrowPanel = 0.75; // outer panels narrower than this in u us
 constexpr int kSnapNStart = 0, kSnapDeltaN = 1, kSnapIncr = 2, kSnapValid = 3, kSnapDisc = 4, kSnapTail = 12,
               kSnapContrib = 20, kSnapActive = 28, kSnapDoubles = 32;
 
+constexpr int kSymInnerChan = 6;
 struct SymFastWS {
-    EngLevel inner, outer;
+    EngLevelT<kSymInnerChan> inner; // the six integrands of a node (the V lobes are halves of the same panels)
+    EngLevel outer;
     LeungOrder on, on1;
     double snap[kSnapDoubles];
     // the warp-uniform context of the point in work (SymFastCtx + the distribution): in shared memory, not
@@ -480,7 +482,7 @@ RB_FN_NOINLINE void sym_gamma_integral(Warp &w, const SymFastCtx<KIND> &cx, doub
             const double x = L15_X[w.lane], wk = L15_WK[w.lane], wd = L15_WD[w.lane];
             double vals[6];
             sym_node<KIND>(cx, n, gamma_peak + half * (0.5 * (pa + pb) + 0.5 * (pb - pa) * x), vals);
-            tile_store_weighted<6>(ws.inner.tile, w.lane, wk, wd, vals);
+            tile_store_weighted<6, kSymInnerChan>(ws.inner.tile, w.lane, wk, wd, vals);
         }
 #else
         for (int l = 0; l < 32; l++) {
@@ -488,14 +490,14 @@ RB_FN_NOINLINE void sym_gamma_integral(Warp &w, const SymFastCtx<KIND> &cx, doub
             const double pa = second ? ta1 : ta0, pb = second ? tb1 : tb0;
             double vals[6];
             sym_node<KIND>(cx, n, gamma_peak + half * (0.5 * (pa + pb) + 0.5 * (pb - pa) * L15_X[l]), vals);
-            tile_store_weighted<6>(ws.inner.tile, l, L15_WK[l], L15_WD[l], vals);
+            tile_store_weighted<6, kSymInnerChan>(ws.inner.tile, l, L15_WK[l], L15_WD[l], vals);
         }
 #endif
         w.n_apply_lanes++;
         warp_fence();
 
         PerChan<double> r0, e0, r1, e1;
-        tile_reduce_pair(ws.inner.tile, 6, 0.5 * (tb0 - ta0) * half, 0.5 * (tb1 - ta1) * half, r0, e0, r1, e1);
+        tile_reduce_pair<kSymInnerChan>(ws.inner.tile, 6, 0.5 * (tb0 - ta0) * half, 0.5 * (tb1 - ta1) * half, r0, e0, r1, e1);
 
 #pragma unroll
         for (int p = 0; p < 2; p++) {

@@ -255,6 +255,10 @@ int launch_kind(DeviceContext &c, BatchArgs a, const ResolvedOptions &o, cudaStr
     // Heyvaerts always runs on the library's second stream, forked from and joined back
     // into `st` with events, so a caller-supplied stream keeps its ordering semantics.
     cudaStream_t st_hey = c.stream_hey;
+    // tuning knob (tools/variant_bench.py): both stages on one stream, one after the other
+    static const bool serial_stages = getenv("RIMPHONY_B200_SERIAL_STAGES") != nullptr;
+    if (serial_stages)
+        st_hey = st;
     unsigned long long *counters = static_cast<unsigned long long *>(c.counters.ptr);
     const bool faithful = (o.mode == RIMPHONY_B200_MODE_FAITHFUL);
     const bool want_sym = (o.coeff_mask & 0x3Fu) != 0;
