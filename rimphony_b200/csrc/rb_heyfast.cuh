@@ -85,6 +85,7 @@ struct HeyFastWS {
     // (see SymFastWS)
     Dist dist;
     double ctx_store[10];
+    JYOrder jy; // J/Y orders of the quasi-resonant inner integral in work (rb_special.cuh)
 };
 
 template <int KIND>
@@ -208,6 +209,14 @@ RB_FN_NOINLINE bool hey_inner_integral(Warp &w, const HeyFastCtx<KIND> &cx, int 
                 else if (cut >= pomega_max)
                     cut = end;
             }
+            // the ends of the range beyond the cut (all of it when cut = 0) are in the J/Y form: its orders
+            // sigma, sigma - 1 are the same for every node of this integral and are prepared once
+            warp_fence();
+            if (cut < end)
+                jy_prepare(v, ws.jy); // every lane writes the same values
+            else
+                ws.jy.sigma = NAN;
+            warp_fence();
             if (cut > 0.0 && cut < end) {
                 stk.push(w, -end, -cut, 0);
                 stk.push(w, cut, end, 0);
@@ -247,7 +256,7 @@ RB_FN_NOINLINE bool hey_inner_integral(Warp &w, const HeyFastCtx<KIND> &cx, int 
                 vals[0] *= x;
                 vals[1] *= x;
             } else {
-                HeyQRIntegrand<KIND, 2> f{cx.d, &g, v, 0};
+                HeyQRIntegrand<KIND, 2> f{cx.d, &g, v, 0, &ws.jy};
                 if (sine_map) {
                     double sin_t, cos_t;
                     sincos(t, &sin_t, &cos_t);
@@ -273,7 +282,7 @@ RB_FN_NOINLINE bool hey_inner_integral(Warp &w, const HeyFastCtx<KIND> &cx, int 
                 vals[0] *= x;
                 vals[1] *= x;
             } else {
-                HeyQRIntegrand<KIND, 2> f{cx.d, &g, v, 0};
+                HeyQRIntegrand<KIND, 2> f{cx.d, &g, v, 0, &ws.jy};
                 if (sine_map) {
                     double sin_t, cos_t;
                     sincos(t, &sin_t, &cos_t);

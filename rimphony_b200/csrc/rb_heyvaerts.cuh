@@ -134,6 +134,7 @@ struct HeyQRIntegrand {
     const HeyGeometry *g;
     double sigma;
     int sel;
+    const JYOrder *jy = nullptr; // the J/Y orders of this sigma, prepared by the caller (product path), or none
 
     RB_FN void eval(double pomega, double (&out)[NV], double x_exact = NAN) const
     {
@@ -155,7 +156,10 @@ struct HeyQRIntegrand {
             y_f = kInverseSqrt3 * gg * (im23 - ip23) * (im13 + ip13);
         } else {
             double js, jsm1, ys, ysm1;
-            bessel_jy_pair(sigma, x, js, jsm1, ys, ysm1);
+            if (jy != nullptr && jy->sigma == sigma)
+                bessel_jy_pair_prepared(*jy, x, js, jsm1, ys, ysm1);
+            else
+                bessel_jy_pair(sigma, x, js, jsm1, ys, ysm1);
             const double jvp = jsm1 - sigma * js * inv_x;
             const double yvp = ysm1 - sigma * ys * inv_x;
             y_h1 = jvp * yvp;

@@ -176,6 +176,164 @@ RB_FN_NOINLINE void bessel_jy_pair(double sigma, double x, double &j_s, double &
     }
 }
 
+// --- J/Y with the order-only work done once -----------------------------------------------------
+// In the quasi-resonant inner integral the order sigma is the OUTER variable: every node of every rule
+// application of an inner integral asks for J and Y of the same two orders.  What depends on the order only
+// (1/Gamma(1 + nu) of the three J series, Temme's gamma functions and trigonometric factors: ~30 % of a node)
+// is prepared once per inner integral; per node one logarithm and one exponential then serve all series
+// ((x/2)^nu for every nu needed is (x/2)^sigma times an integer power of x/2).  Same series, same values to
+// rounding as bessel_jy_pair().
+struct TemmeOrder {
+    double mu, gam1, gam2;
+    double c_p, c_q; // 1 / (pi Gamma(1 + mu)) ... as gampl, gammi enter p and q
+    double fact, r;  // pi mu / sin(pi mu), pi (pi mu / 2) (sin(pi mu / 2) / (pi mu / 2))^2
+};
+struct JYOrder {
+    double sigma;    // the order this was prepared for (NaN: not prepared)
+    double rg_s, rg_sm1, rg_a; // 1 / Gamma(1 + sigma), 1 / Gamma(sigma), 1 / Gamma(2 - sigma)
+    double sin_api, cos_api;   // sin, cos of (1 - sigma) pi (sigma < 1/2)
+    TemmeOrder t0, t1;         // mu = sigma - 1 - m; or mu = sigma and mu = -sigma for sigma < 1/2
+    int m;                     // upward recurrences from Y_mu, Y_{mu+1}; -1: sigma < 1/2
+};
+
+RB_FN void temme_prepare(double mu, TemmeOrder &t)
+{
+    const double eps = DBL_EPSILON;
+    double gampl, gammi;
+    gamma_pair(mu, t.gam1, t.gam2, gampl, gammi);
+    t.mu = mu;
+    const double pimu = kPi * mu;
+    t.fact = (fabs(pimu) < eps) ? 1.0 : pimu / sin(pimu);
+    t.c_p = 1.0 / (gampl * kPi);
+    t.c_q = 1.0 / (kPi * gammi);
+    const double pimu2 = 0.5 * pimu;
+    const double fact3 = (fabs(pimu2) < eps) ? 1.0 : sin(pimu2) / pimu2;
+    t.r = kPi * pimu2 * fact3 * fact3;
+}
+
+RB_FN_NOINLINE void jy_prepare(double sigma, JYOrder &o)
+{
+    o.sigma = sigma;
+    o.rg_s = rgamma1p(sigma);
+    o.rg_sm1 = rgamma1p(sigma - 1.0);
+    const double lo = sigma - 1.0;
+    if (lo >= -0.5) {
+        const double m = floor(lo + 0.5);
+        o.m = (int)m;
+        temme_prepare(lo - m, o.t0);
+        o.t1 = o.t0;
+        o.rg_a = o.sin_api = o.cos_api = 0.0;
+    } else {
+        o.m = -1;
+        temme_prepare(sigma, o.t0);
+        temme_prepare(-sigma, o.t1);
+        const double a = 1.0 - sigma;
+        o.rg_a = rgamma1p(a);
+        o.sin_api = sin(a * kPi);
+        o.cos_api = cos(a * kPi);
+    }
+}
+
+// sum_k (-x^2/4)^k / (k! (1 + nu)_k): the ascending series of J_nu without its prefactor
+RB_FN double bessel_j_sum(double nu, double q)
+{
+    double term = 1.0, sum = 1.0;
+#pragma unroll 1
+    for (int k = 1; k < 200; k++) {
+        term *= q * rb_rcp(k * (k + nu));
+        sum += term;
+        if (fabs(term) < 1e-17 * fabs(sum))
+            break;
+    }
+    return sum;
+}
+
+// Temme's series with the order prepared; d = -ln(x/2), big_e = (x/2)^-mu, inv_e = (x/2)^mu
+RB_FN void bessel_y_temme_prepared(const TemmeOrder &t, double x, double d, double big_e, double inv_e, double &y_mu,
+                                   double &y_mu1)
+{
+    const double eps = DBL_EPSILON;
+    const double mu = t.mu;
+    const double e = mu * d;
+    const double cosh_e = 0.5 * (big_e + inv_e);
+    double fact2; // sinh(e) / e
+    if (fabs(e) < 0.3) {
+        const double e2 = e * e;
+        fact2 = 1.0 + e2 * (1.0 / 6.0 + e2 * (1.0 / 120.0 + e2 * (1.0 / 5040.0 + e2 * (1.0 / 362880.0 +
+                e2 * (1.0 / 39916800.0 + e2 * (1.0 / 6227020800.0))))));
+    } else
+        fact2 = 0.5 * (big_e - inv_e) * rb_rcp(e);
+    double ff = 2.0 / kPi * t.fact * (t.gam1 * cosh_e + t.gam2 * fact2 * d);
+    double p = big_e * t.c_p;
+    double q = inv_e * t.c_q;
+    const double x2 = 0.5 * x;
+    double c = 1.0;
+    const double dd = -x2 * x2;
+    double sum = ff + t.r * q;
+    double sum1 = p;
+#pragma unroll 1
+    for (int i = 1; i < 500; i++) {
+        const double im = i - mu, ip = i + mu;
+        const double rr = rb_rcp(im * ip);
+        ff = (i * ff + p + q) * rr;
+        c *= dd * rb_rcp((double)i);
+        p *= ip * rr;
+        q *= im * rr;
+        const double del = c * (ff + t.r * q);
+        sum += del;
+        const double del1 = c * p - i * del;
+        sum1 += del1;
+        if (fabs(del) < (1.0 + fabs(sum)) * eps * 0.1)
+            break;
+    }
+    y_mu = -sum;
+    y_mu1 = -sum1 * (2.0 * rb_rcp(x));
+}
+
+// bessel_jy_pair() for the prepared order o.sigma
+RB_FN_NOINLINE void bessel_jy_pair_prepared(const JYOrder &o, double x, double &j_s, double &j_sm1, double &y_s,
+                                            double &y_sm1)
+{
+    const double sigma = o.sigma;
+    if (!(x > 0.0) || !(sigma > 0.0)) {
+        j_s = j_sm1 = y_s = y_sm1 = NAN;
+        return;
+    }
+    const double x2 = 0.5 * x;
+    const double big_l = rb_log(x2);
+    const double ps = rb_exp(sigma * big_l); // (x/2)^sigma
+    const double inv_ps = rb_rcp(ps);
+    const double inv_x2 = rb_rcp(x2);
+    const double q = -x2 * x2;
+    j_s = ps * o.rg_s * bessel_j_sum(sigma, q);
+    j_sm1 = ps * inv_x2 * o.rg_sm1 * bessel_j_sum(sigma - 1.0, q);
+    const double d = -big_l;
+    if (o.m >= 0) {
+        // mu = sigma - 1 - m: (x/2)^-mu = (x/2)^(m+1) / (x/2)^sigma
+        double pw = x2;
+        for (int i = 0; i < o.m; i++)
+            pw *= x2;
+        const double big_e = pw * inv_ps;
+        double ya, yb;
+        bessel_y_temme_prepared(o.t0, x, d, big_e, rb_rcp(big_e), ya, yb); // Y_mu, Y_{mu+1}
+        for (int i = 1; i <= o.m; i++) {
+            const double yn = (o.t0.mu + i) * inv_x2 * yb - ya;
+            ya = yb;
+            yb = yn;
+        }
+        y_sm1 = ya;
+        y_s = yb;
+    } else {
+        // sigma < 1/2: Y_sigma directly (mu = sigma), Y_{sigma-1} = Y_{-a}, a = 1 - sigma, by reflection (mu = -sigma)
+        double ys, tmp, ym, ya;
+        bessel_y_temme_prepared(o.t0, x, d, inv_ps, ps, ys, tmp);
+        bessel_y_temme_prepared(o.t1, x, d, ps, inv_ps, ym, ya); // Y_{-sigma}, Y_{1-sigma}
+        y_s = ys;
+        const double ja = x2 * inv_ps * o.rg_a * bessel_j_sum(1.0 - sigma, q);
+        y_sm1 = o.sin_api * ja + o.cos_api * ya;
+    }
+}
+
 constexpr int kISeriesMax = 48;
 // prod_{j<=k} 1/(j (j + nu)), rows nu = 1/3, -1/3, 2/3, -2/3; column k (generated with mpmath): the ascending
 // series of I_nu is (g/2)^nu / Gamma(1 + nu) sum_k ISERIES_COEF[.][k] q^k, q = (g/2)^2
