@@ -82,10 +82,10 @@ RB_FN double log_pitch_term(double k, double sin2)
 // calc_f and calc_f_derivatives in one go.  `sin2_exact`: sin^2(xi) when the caller knows it
 // without the cancellation of 1 - cos^2 (the Heyvaerts product path, where |cos xi| -> 1 at the
 // ends of the inner range and the rounded 1 - cos^2 turns into 0 or a negative number); NaN =
-// compute it from cos_xi as the reference does.
+// compute it from cos_xi as the reference does.  `sqrt_g2m1`: sqrt(gamma^2 - 1) when the caller has it already.
 template <int KIND>
 RB_FN void dist_eval(const Dist &d, double gamma, double cos_xi, double &f, double &dfdg, double &dfdcx,
-                     double sin2_exact = NAN)
+                     double sin2_exact = NAN, double sqrt_g2m1 = NAN)
 {
     if (KIND == kDistPowerLaw) {
         if (gamma < d.gamma_min || gamma > d.gamma_max) {
@@ -94,7 +94,7 @@ RB_FN void dist_eval(const Dist &d, double gamma, double cos_xi, double &f, doub
         }
         const double g2m1 = gamma * gamma - 1.0;
         // norm gamma^-p rb_exp(-gamma/gc) / (gamma^2 beta),  gamma^2 beta = gamma rb_sqrt(gamma^2 - 1)
-        const double sq = rb_sqrt(g2m1);
+        const double sq = (sqrt_g2m1 == sqrt_g2m1) ? sqrt_g2m1 : rb_sqrt(g2m1);
         const double inv = rb_rcp(gamma * sq); // 1 / (gamma^2 beta); 1 / gamma = inv sq, 1 / (gamma^2 - 1) = (inv gamma)^2
         const double ig = inv * gamma;
         f = d.norm * rb_exp(-d.p * rb_log(gamma) - gamma * d.inv_gamma_cutoff) * inv;
@@ -111,7 +111,7 @@ RB_FN void dist_eval(const Dist &d, double gamma, double cos_xi, double &f, doub
         }
         const double sin2 = (sin2_exact == sin2_exact) ? sin2_exact : 1.0 - cos_xi * cos_xi;
         const double g2m1 = gamma * gamma - 1.0;
-        const double sq = rb_sqrt(g2m1);
+        const double sq = (sqrt_g2m1 == sqrt_g2m1) ? sqrt_g2m1 : rb_sqrt(g2m1);
         const double inv = rb_rcp(gamma * sq); // 1 / (gamma^2 beta); 1 / gamma = inv sq, 1 / (gamma^2 - 1) = (inv gamma)^2
         const double ig = inv * gamma;
         f = d.norm * rb_exp(log_pitch_term(d.k, sin2) - d.p * rb_log(gamma) - gamma * d.inv_gamma_cutoff) * inv;

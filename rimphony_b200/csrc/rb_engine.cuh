@@ -419,6 +419,47 @@ RB_FN_NOINLINE void tile_reduce(const double *tile, int nv, double hl, PerChan<d
     }
 }
 
+// The outer level without a tile: its node values (inner integrals) arrive one after the other, and what the
+// rule needs of them are three sums per channel -- sum wk G (Kronrod), sum (wk - wg) G (Kronrod - Gauss) and
+// sum |wk G| -- so they are accumulated as they arrive instead of being parked and reduced (4.6 KB of shared
+// memory per warp less: the Symphony kernel's CTAs per SM were bound by it).
+struct OuterAcc {
+    double k[kEngChan], d[kEngChan], a[kEngChan];
+};
+struct OuterLevel {
+    OuterAcc acc;
+    double stk_a[kEngStack];
+    double stk_b[kEngStack];
+    int stk_tag[kEngStack];
+};
+RB_FN void acc_clear(const Warp &w, OuterAcc &acc)
+{
+#ifdef RB_DEVICE_BUILD
+    if (w.lane < 3 * kEngChan)
+        acc.k[w.lane] = 0.0; // k, d, a are contiguous
+#else
+    (void)w;
+    for (int i = 0; i < kEngChan; i++)
+        acc.k[i] = acc.d[i] = acc.a[i] = 0.0;
+#endif
+}
+// one node value of channel c (called by one lane per channel)
+RB_FN void acc_add(OuterAcc &acc, int c, double wa, double wb, double v)
+{
+    const double t = wa * v;
+    acc.k[c] += t;
+    acc.d[c] += wb * v;
+    acc.a[c] += fabs(t);
+}
+RB_FN void acc_reduce(const OuterAcc &acc, double hl, PerChan<double> &r, PerChan<double> &e)
+{
+    RB_FOR_CHAN(c, kEngChan)
+    {
+        r[c] = acc.k[c] * hl;
+        e[c] = quad_error(acc.d[c], acc.a[c], hl);
+    }
+}
+
 // Warp vote over the channels 0..nv-1.
 RB_FN bool chan_all(const PerChan<bool> &ok, int nv)
 {
@@ -441,8 +482,8 @@ struct PanelStack {
     } store;
     int sp;
 
-    template <int CH>
-    RB_FN void reset(EngLevelT<CH> *level)
+    template <class Level>
+    RB_FN void reset(Level *level)
     {
         store.stk_a = level->stk_a;
         store.stk_b = level->stk_b;

@@ -133,8 +133,8 @@ RB_FN_NOINLINE bool hey_inner_integral(Warp &w, const HeyFastCtx<KIND> &cx, int 
     double nr_sigma_min = 0.0;
     if (which == kHeyNR) {
         // heyvaerts.rs:213-250: sigma in [sigma_min, sigma_min^1.5 / sqrt(3)], in t = ln sigma
-        const double sigma_min = sqrt(v * v + g.sigma0_sq);
-        const double sigma_max = kInverseSqrt3 * sigma_min * sqrt(sigma_min);
+        const double sigma_min = rb_sqrt(v * v + g.sigma0_sq);
+        const double sigma_max = kInverseSqrt3 * sigma_min * rb_sqrt(sigma_min);
         if (!(sigma_max > sigma_min)) {
             empty = true;
         } else {
@@ -142,8 +142,8 @@ RB_FN_NOINLINE bool hey_inner_integral(Warp &w, const HeyFastCtx<KIND> &cx, int 
             // lower end (x -> 0, where the integrand has algebraic end-point behaviour, strongest
             // around the cusp pomega*) t is linear in x; far out it is ln sigma.
             nr_sigma_min = sigma_min;
-            const double ratio = kInverseSqrt3 * sqrt(sigma_min);
-            const double t_lo = 0.0, t_hi = rb_log(ratio + sqrt((ratio - 1.0) * (ratio + 1.0)));
+            const double ratio = kInverseSqrt3 * rb_sqrt(sigma_min);
+            const double t_lo = 0.0, t_hi = rb_log(ratio + rb_sqrt((ratio - 1.0) * (ratio + 1.0)));
             int n_seed = (int)ceil((t_hi - t_lo) / kHeyInnerWidth);
             n_seed = n_seed < 1 ? 1 : (n_seed > 8 ? 8 : n_seed);
             for (int k = n_seed - 1; k >= 0; k--) // the lowest panel (largest values) is popped first
@@ -151,8 +151,8 @@ RB_FN_NOINLINE bool hey_inner_integral(Warp &w, const HeyFastCtx<KIND> &cx, int 
         }
     } else {
         // heyvaerts.rs:262-296: pomega in [-pomega_max, pomega_max]
-        const double pomega_max_phys = sqrt(kThreeTwoThirds * rb_cbrt(v) * v - g.sigma0_sq);
-        const double pomega_max_qr = sqrt(v * v - g.sigma0_sq);
+        const double pomega_max_phys = rb_sqrt(kThreeTwoThirds * rb_cbrt(v) * v - g.sigma0_sq);
+        const double pomega_max_qr = rb_sqrt(v * v - g.sigma0_sq);
         const double pomega_max = fmin(pomega_max_phys, pomega_max_qr);
         if (!(pomega_max > 0.0) && pomega_max == pomega_max)
             empty = true;
@@ -166,9 +166,9 @@ RB_FN_NOINLINE bool hey_inner_integral(Warp &w, const HeyFastCtx<KIND> &cx, int 
             const double x_end_sq = v * v - g.sigma0_sq - pomega_max * pomega_max;
             bool g_reaches_cutoff = true;
             if (x_end_sq > 0.0) {
-                const double x_end = sqrt(x_end_sq);
+                const double x_end = rb_sqrt(x_end_sq);
                 const double d_end = v - x_end;
-                g_reaches_cutoff = !(kSqrt8Over3 * d_end * sqrt(d_end) / sqrt(x_end) < kGApproximationCutoff);
+                g_reaches_cutoff = !(kSqrt8Over3 * d_end * rb_sqrt(rb_div(d_end, x_end)) < kGApproximationCutoff);
             }
             if (g_reaches_cutoff) {
                 const double big_k = kGApproximationCutoff / kSqrt8Over3;
@@ -176,16 +176,17 @@ RB_FN_NOINLINE bool hey_inner_integral(Warp &w, const HeyFastCtx<KIND> &cx, int 
 #pragma unroll 1
                 for (int it = 0; it < 40; it++) {
                     const double d = v - x;
-                    const double h = d * sqrt(d) - big_k * sqrt(x);
+                    const double sd = rb_sqrt(d), sx = rb_sqrt(x);
+                    const double h = d * sd - big_k * sx;
                     if (h > 0.0)
                         lo = x;
                     else
                         hi = x;
-                    const double dh = -1.5 * sqrt(d) - 0.5 * big_k * rb_rcp(sqrt(x));
+                    const double dh = -1.5 * sd - 0.5 * big_k * rb_rcp(sx);
                     double xn = x - rb_div(h, dh);
                     if (!(xn > lo && xn < hi))
                         xn = 0.5 * (lo + hi);
-                    if (fabs(xn - x) <= 1e-14 * v) {
+                    if (fabs(xn - x) <= 1e-10 * v) { // (a panel boundary)
                         x = xn;
                         break;
                     }
@@ -193,7 +194,7 @@ RB_FN_NOINLINE bool hey_inner_integral(Warp &w, const HeyFastCtx<KIND> &cx, int 
                 }
                 const double p2 = v * v - g.sigma0_sq - x * x;
                 if (p2 > 0.0) {
-                    const double pg = sqrt(p2);
+                    const double pg = rb_sqrt(p2);
                     if (pg < pomega_max)
                         cut = pg;
                 } else

@@ -49,7 +49,8 @@ struct HeyNode {
         const double t = g.sigma0 * g.sin_th;
         const double inv_t = rb_rcp(t);
         const double gamma = (sigma - pomega * g.cos_th) * inv_t;
-        double mu = rb_div(sigma * g.cos_th - pomega, t * rb_sqrt(gamma * gamma - 1.0));
+        const double sq = rb_sqrt(gamma * gamma - 1.0); // gamma beta: also what dist_eval and d cos(xi) / d sigma need
+        double mu = rb_div(sigma * g.cos_th - pomega, t * sq);
 
         // sin^2(xi) = 1 - mu^2 = x^2 sin^2(theta) / ((sigma - pomega cos(theta))^2 - t^2) identically.
         // Where the caller knows x without cancellation (the product path's substitutions) this
@@ -72,14 +73,15 @@ struct HeyNode {
 #endif
 
         double f, dfdg, dfdcxi;
-        dist_eval<KIND>(d, gamma, mu, f, dfdg, dfdcxi, sin2);
+        dist_eval<KIND>(d, gamma, mu, f, dfdg, dfdcxi, sin2, sq);
         const double g_term = dfdg * inv_t;
         double mu_term = 0.0;
         if (dfdcxi != 0.0) {
             const double q = sigma - pomega * g.cos_th;
             const double r = pomega - sigma * g.cos_th;
             const double u = q * q - t * t;
-            const double dcxi_dsigma = rb_div(q * u * g.cos_th + u * r + r * t * t, u * rb_sqrt(u) * q);
+            // sqrt(u) = sigma0 sin(theta) sqrt(gamma^2 - 1)
+            const double dcxi_dsigma = rb_div(q * u * g.cos_th + u * r + r * t * t, u * (t * sq) * q);
             mu_term = dcxi_dsigma * dfdcxi;
         }
         dfds = g_term + mu_term;

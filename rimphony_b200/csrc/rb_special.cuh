@@ -353,13 +353,22 @@ RB_FN void bessel_i_thirds(double g, double &ip13, double &im13, double &ip23, d
     const double q = 0.25 * g * g;
     double qk = 1.0;
     double s0 = 1.0, s1 = 1.0, s2 = 1.0, s3 = 1.0;
+#ifdef RB_LEAN_MATH
+    // What the elements need are the differences I_-nu - I_nu = (2/pi) sin(nu pi) K_nu, which are ~ pi exp(-2 g) of
+    // the sums: a truncation at 1e-7 / (1 + 42 q^4) <= 3e-7 pi exp(-4 sqrt(q)) of the sum (q <= 25) gives them to
+    // 3e-7, with 3-17 terms where 1e-17 takes 5-24.
+    const double q2 = q * q;
+    const double tol = 1e-7 * rb_rcp(1.0 + 42.0 * q2 * q2);
+#else
+    const double tol = 1e-17;
+#endif
     for (int k = 1; k < kISeriesMax; k++) {
         qk *= q;
         s0 = fma(ISERIES_COEF[0][k], qk, s0);
         s1 = fma(ISERIES_COEF[1][k], qk, s1);
         s2 = fma(ISERIES_COEF[2][k], qk, s2);
         s3 = fma(ISERIES_COEF[3][k], qk, s3);
-        if (ISERIES_COEF[3][k] * qk < 1e-17 * s3) // nu = -2/3 has the largest terms of the four (its sum is within 2.5 of the others')
+        if (ISERIES_COEF[3][k] * qk < tol * s3) // nu = -2/3 has the largest terms of the four (its sum is within 2.5 of the others')
             break;
     }
     const double c = rb_cbrt(0.5 * g); // (g/2)^(1/3)

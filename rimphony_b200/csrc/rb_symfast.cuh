@@ -72,7 +72,7 @@ constexpr int kSnapNStart = 0, kSnapDeltaN = 1, kSnapIncr = 2, kSnapValid = 3, k
 constexpr int kSymInnerChan = 6;
 struct SymFastWS {
     EngLevelT<kSymInnerChan> inner; // the six integrands of a node (the V lobes are halves of the same panels)
-    EngLevel outer;
+    OuterLevel outer; // the n level: running sums instead of a tile (rb_engine.cuh)
     LeungOrder on, on1;
     double snap[kSnapDoubles];
     // the warp-uniform context of the point in work (SymFastCtx + the distribution): in shared memory, not
@@ -194,7 +194,7 @@ RB_FN void sym_node(const SymFastCtx<KIND> &cx, double n, double gamma, double (
     const double njp = big_n * djn;
 
     double f, dfdg, dfdcx;
-    dist_eval<KIND>(*cx.d, gamma, cos_xi, f, dfdg, dfdcx);
+    dist_eval<KIND>(*cx.d, gamma, cos_xi, f, dfdg, dfdcx, NAN, gamma * beta); // sqrt(gamma^2 - 1) = gamma beta
     const double dfdcx_factor = rb_div(beta * costh - cos_xi, gamma - rb_rcp(gamma));
     const double f_abs = dfdg + dfdcx_factor * dfdcx;
 
@@ -241,20 +241,7 @@ RB_FN_NOINLINE void sym_gamma_integral(Warp &w, const SymFastCtx<KIND> &cx, doub
             const double th = sqrt((1.0 - x0) * (1.0 + x0));
             const double exponent = 2.0 * n * (rb_log(rb_div(1.0 + th, x0)) - th);
             if (exponent > kNegligibleExponent) {
-                double *ot = ws.outer.tile;
-#ifdef RB_DEVICE_BUILD
-                if (w.lane < kEngChan)
-#else
-                for (int l = 0; l < kEngChan; l++)
-#endif
-                {
-#ifdef RB_DEVICE_BUILD
-                    const int l = w.lane;
-#endif
-                    ot[l * kEngRow + col] = 0.0;
-                    ot[(kEngChan + l) * kEngRow + col] = 0.0;
-                }
-                return;
+                return; // adds nothing to the sums of the outer rule
             }
         }
     }
@@ -540,8 +527,9 @@ RB_FN_NOINLINE void sym_gamma_integral(Warp &w, const SymFastCtx<KIND> &cx, doub
 #ifdef RB_TRACE_GEND
     RB_TRACE_GEND(n, w.n_apply_lanes);
 #endif
-    // park the eight accumulators in the outer tile
-    double *ot = ws.outer.tile;
+    // add the eight accumulators to the sums of the outer rule
+    (void)col;
+    warp_fence();
 #ifdef RB_DEVICE_BUILD
     if ((w.lane & 3) == 0)
 #endif
@@ -549,17 +537,14 @@ RB_FN_NOINLINE void sym_gamma_integral(Warp &w, const SymFastCtx<KIND> &cx, doub
         RB_FOR_CHAN(c, 6)
         {
             if (c < 4) {
-                const double v = sum_l[c] + sum_r[c];
-                ot[c * kEngRow + col] = wa * v;
-                ot[(kEngChan + c) * kEngRow + col] = wb * v;
+                acc_add(ws.outer.acc, c, wa, wb, sum_l[c] + sum_r[c]);
             } else {
-                ot[c * kEngRow + col] = wa * sum_r[c];
-                ot[(kEngChan + c) * kEngRow + col] = wb * sum_r[c];
-                ot[(c + 2) * kEngRow + col] = wa * sum_l[c];
-                ot[(kEngChan + c + 2) * kEngRow + col] = wb * sum_l[c];
+                acc_add(ws.outer.acc, c, wa, wb, sum_r[c]);
+                acc_add(ws.outer.acc, c + 2, wa, wb, sum_l[c]);
             }
         }
     }
+    warp_fence();
 }
 
 // Where G(n) is not smooth in n.  At the peak of the gamma window eps = (n - z)/n falls like
@@ -685,7 +670,7 @@ RB_FN void symphony_point_fast(Warp &w, const Dist &dist, double s, double theta
 
     // the first 30 harmonics, discretely (symphony.rs:96-108): a tile with unit weights
     warp_fence();
-    tile_clear(w, ws.outer.tile);
+    acc_clear(w, ws.outer.acc);
     warp_fence();
     {
         int col = 0;
@@ -694,7 +679,7 @@ RB_FN void symphony_point_fast(Warp &w, const Dist &dist, double s, double theta
     }
     warp_fence();
     PerChan<double> disc, unused;
-    tile_reduce(ws.outer.tile, kEngChan, 1.0, disc, unused);
+    acc_reduce(ws.outer.acc, 1.0, disc, unused);
 
     // The rest, treating n as continuous (symphony.rs:124-140).  The chunks [n_start,
     // n_start + delta_n] and the rules that grow delta_n and end the loop are the
@@ -773,24 +758,20 @@ RB_FN void symphony_point_fast(Warp &w, const Dist &dist, double s, double theta
 
         // d G / d n at the start of the chunk
         warp_fence();
-        tile_clear(w, ws.outer.tile);
+        acc_clear(w, ws.outer.acc);
         warp_fence();
         {
             const double dn = kDerivStep * n_lo_chunk;
-            sym_gamma_integral<KIND>(w, cx, n_lo_chunk - dn, tile_col(0), -0.5 / dn, 0.0);
-            sym_gamma_integral<KIND>(w, cx, n_lo_chunk + dn, tile_col(1), 0.5 / dn, 0.0);
+            // Kronrod sum: the central difference; the second sum: the mean of the two probes, G at the start
+            sym_gamma_integral<KIND>(w, cx, n_lo_chunk - dn, tile_col(0), -0.5 / dn, 0.5);
+            sym_gamma_integral<KIND>(w, cx, n_lo_chunk + dn, tile_col(1), 0.5 / dn, 0.5);
         }
         warp_fence();
         PerChan<double> deriv, unused2;
-        tile_reduce(ws.outer.tile, kEngChan, 1.0, deriv, unused2);
-        // G at the start of the chunk, from the same two probes: columns 0 and 1 hold -G(n - dn) / (2 dn) and
-        // G(n + dn) / (2 dn)
+        acc_reduce(ws.outer.acc, 1.0, deriv, unused2);
+        // G at the start of the chunk, from the same two probes
         PerChan<double> g_start;
-        RB_FOR_CHAN(c, kEngChan)
-        {
-            const double *ot = ws.outer.tile;
-            g_start[c] = kDerivStep * n_lo_chunk * (ot[c * kEngRow + tile_col(1)] - ot[c * kEngRow + tile_col(0)]);
-        }
+        RB_FOR_CHAN(c, kEngChan) { g_start[c] = ws.outer.acc.d[c]; }
         PerChan<bool> grow_c;
         RB_FOR_CHAN(c, kEngChan)
         {
@@ -856,8 +837,6 @@ RB_FN void symphony_point_fast(Warp &w, const Dist &dist, double s, double theta
         }
         const bool light = chunk_no > 0 && chan_all(minor, kEngChan);
         warp_fence();
-        tile_clear(w, ws.outer.tile);
-        int filled = 0;
         while (stk.sp > 0) {
             double ua, ub;
             int tag;
@@ -870,11 +849,8 @@ RB_FN void symphony_point_fast(Warp &w, const Dist &dist, double s, double theta
             const double *rx = narrow ? GK7_X : GK15_X;
             const double *rwk = narrow ? GK7_WK : GK15_WK;
             const double *rwd = narrow ? GK7_WD : GK15_WD;
-            if (n_nodes < filled) {
-                tile_clear(w, ws.outer.tile);
-                warp_fence();
-            }
-            filled = n_nodes;
+            acc_clear(w, ws.outer.acc);
+            warp_fence();
 #pragma unroll 1
             for (int j = 0; j < n_nodes; j++) {
                 const double n = rb_exp(uc + uhl * rx[j]);
@@ -882,7 +858,7 @@ RB_FN void symphony_point_fast(Warp &w, const Dist &dist, double s, double theta
             }
             warp_fence();
             PerChan<double> r, e;
-            tile_reduce(ws.outer.tile, kEngChan, uhl, r, e);
+            acc_reduce(ws.outer.acc, uhl, r, e);
 
             PerChan<bool> ok;
             RB_FOR_CHAN(c, kEngChan)
