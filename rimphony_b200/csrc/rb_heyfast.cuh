@@ -168,30 +168,26 @@ RB_FN_NOINLINE bool hey_inner_integral(Warp &w, const HeyFastCtx<KIND> &cx, int 
             if (x_end_sq > 0.0) {
                 const double x_end = rb_sqrt(x_end_sq);
                 const double d_end = v - x_end;
-                g_reaches_cutoff = !(kSqrt8Over3 * d_end * rb_sqrt(rb_div(d_end, x_end)) < kGApproximationCutoff);
+                // g < 10  <=>  (sigma - x)^3 < (10 / (sqrt(8)/3))^2 x
+                g_reaches_cutoff = !(d_end * d_end * d_end < (kGApproximationCutoff / kSqrt8Over3) * (kGApproximationCutoff / kSqrt8Over3) * x_end);
             }
             if (g_reaches_cutoff) {
-                const double big_k = kGApproximationCutoff / kSqrt8Over3;
-                double lo = 0.0, hi = v, x = 0.5 * v;
+                // (v - x)^1.5 = K sqrt(x), K = 10 / (sqrt(8)/3): with u = x / v the cubic (1 - u)^3 v^2 - K^2 u = 0,
+                // convex and falling on [0, 1]: Newton from u = 0 approaches the root from the left, no square roots
+                constexpr double big_k2 = (kGApproximationCutoff / kSqrt8Over3) * (kGApproximationCutoff / kSqrt8Over3);
+                const double v2 = v * v;
+                double u = 0.0;
 #pragma unroll 1
-                for (int it = 0; it < 40; it++) {
-                    const double d = v - x;
-                    const double sd = rb_sqrt(d), sx = rb_sqrt(x);
-                    const double h = d * sd - big_k * sx;
-                    if (h > 0.0)
-                        lo = x;
-                    else
-                        hi = x;
-                    const double dh = -1.5 * sd - 0.5 * big_k * rb_rcp(sx);
-                    double xn = x - rb_div(h, dh);
-                    if (!(xn > lo && xn < hi))
-                        xn = 0.5 * (lo + hi);
-                    if (fabs(xn - x) <= 1e-10 * v) { // (a panel boundary)
-                        x = xn;
+                for (int it = 0; it < 60; it++) {
+                    const double w1 = 1.0 - u;
+                    const double w2 = w1 * w1 * v2;
+                    const double un = u + rb_div(w1 * w2 - big_k2 * u, 3.0 * w2 + big_k2);
+                    const bool done = fabs(un - u) <= 1e-10; // (a panel boundary)
+                    u = un;
+                    if (done)
                         break;
-                    }
-                    x = xn;
                 }
+                const double x = u * v;
                 const double p2 = v * v - g.sigma0_sq - x * x;
                 if (p2 > 0.0) {
                     const double pg = rb_sqrt(p2);
