@@ -138,7 +138,7 @@ __global__ void __launch_bounds__(kThreadsPerBlock, 4) k_symphony_diag(BatchArgs
 #define RB_FAST_BLOCKS 5 // resident CTAs per SM the product kernels are compiled for (96 registers; +5 % over 4)
 #endif
 #ifndef RB_HEY_BLOCKS
-#define RB_HEY_BLOCKS 10 // the Heyvaerts kernel (48 registers; its tiles have two channel rows, 14 KB per CTA): 5 -> 10 CTAs per SM is -13 % kernel time, 12 and 16 are slower again
+#define RB_HEY_BLOCKS 8 // the Heyvaerts kernel (64 registers; its tiles have two channel rows, 14 KB per CTA).  5 -> 8 CTAs per SM: -13 % kernel time; 10 (48 registers) is as fast but its 768 B of stack per thread x 1280 threads x 148 SMs no longer fit the L2 and 0.7 MB per point go to DRAM (0.1 MB at 8)
 #endif
 #ifndef RB_FAST_WARPS
 #define RB_FAST_WARPS 4 // warps per CTA of the product kernels
