@@ -271,3 +271,47 @@ extern "C" double emu_symphony_diag(int kind, const double *params, int n_params
     }
     return NAN;
 }
+
+// --- building blocks of the product path, one at a time (tests/test_device_headers_on_host.py) -----------
+// what: 0 rb_exp, 1 rb_log, 2 rb_rcp, 3 rb_sqrt (out[0]); 4 rb_div(a, b)
+extern "C" double emu_lean_math(int what, double a, double b)
+{
+    switch (what) {
+    case 0: return rb_exp(a);
+    case 1: return rb_log(a);
+    case 2: return rb_rcp(a);
+    case 3: return rb_sqrt(a);
+    default: return rb_div(a, b);
+    }
+}
+
+// J_n(x), J_{n+1}(x) twice: out4 = {single n, single n + 1, pair n, pair n + 1}.  Integer orders below 29 go
+// through the Miller recurrences, orders >= 30 through pkgw_bessel_j and the shared-coefficient Debye pair.
+extern "C" void emu_bessel_pair(double n, double x, double *out4)
+{
+    LeungOrder o0, o1;
+    leung_prepare(n, o0);
+    leung_prepare(n + 1.0, o1);
+    out4[0] = leung_j(o0, x);
+    out4[1] = leung_j(o1, x);
+    if (o0.kind == kOrderInteger && o1.kind == kOrderInteger) {
+        bessel_jn_pair_small_int(o0.nint, x, out4[2], out4[3]);
+    } else {
+        double jv[2];
+        leung_j_pair_below(o0, o1, x, jv);
+        out4[2] = jv[0];
+        out4[3] = jv[1];
+    }
+}
+
+// J_sigma, J_{sigma-1}, Y_sigma, Y_{sigma-1} at x: out8 = {plain x 4, prepared-order x 4}
+extern "C" void emu_jy_pair(double sigma, double x, double *out8)
+{
+    bessel_jy_pair(sigma, x, out8[0], out8[1], out8[2], out8[3]);
+    JYOrder o;
+    jy_prepare(sigma, o);
+    bessel_jy_pair_prepared(o, x, out8[4], out8[5], out8[6], out8[7]);
+}
+
+// I_{1/3}, I_{-1/3}, I_{2/3}, I_{-2/3} at g
+extern "C" void emu_i_thirds(double g, double *out4) { bessel_i_thirds(g, out4[0], out4[1], out4[2], out4[3]); }
