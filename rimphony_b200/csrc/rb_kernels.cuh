@@ -48,11 +48,19 @@ __global__ void __launch_bounds__(kThreadsPerBlock, FUSED ? 3 : 4) k_symphony(Ba
 
     for (;;) {
         long long i = next_point(a.next, w.lane);
-        const long long slot = i;
+        long long slot = i;
+        int acc = -1; // >= 0: this warp finishes ONE accumulator of a handed point
         if (a.from_reroute_list) {
-            if (i >= (long long)*a.reroute_count)
+            // The faithful continuation (fidelity guard of rb_symfast.cuh).  A ticket is (handed point, accumulator):
+            // the 2-4 accumulators of a point that are still being integrated replay the reference's sequence
+            // independently of each other (100-250 k rule applications each), so each gets its own warp; the warp
+            // that finishes last puts the point together.  With fewer handed points than warps (any batch below
+            // ~1e5 points) the launch is as long as its longest chain, which this cuts by the number of chains.
+            slot = i >> 3;
+            acc = (int)(i & 7);
+            if (slot >= (long long)*a.reroute_count)
                 break;
-            i = a.reroute_list[i];
+            i = a.reroute_list[slot];
         } else if (i >= a.n)
             break;
         w.status = 0;
@@ -67,12 +75,43 @@ __global__ void __launch_bounds__(kThreadsPerBlock, FUSED ? 3 : 4) k_symphony(Ba
         bool resumed = false;
         if constexpr (!FUSED) {
             if (a.from_reroute_list) {
-                const double *snap = a.handover + (size_t)slot * kSnapDoubles;
+                double *snap = a.handover + (size_t)slot * kSnapDoubles;
                 if (snap[kSnapValid] == 1.0) { // resume the chunk loop where the product path stopped
-                    symphony_tail_faithful<KIND, kSymGammaCap, kSymNCap>(w, d, a.s[i], a.theta[i], a.eps_gamma, a.eps_n,
-                                                                         ws, snap, out6, lobes4);
+                    const unsigned active = (unsigned)snap[kSnapActive];
+                    if (active != 0u) {
+                        if (!((active >> acc) & 1u))
+                            continue; // nothing to integrate for this accumulator: its total is already in the record
+                        const double total = symphony_tail_faithful_one<KIND, kSymGammaCap, kSymNCap>(
+                            w, d, a.s[i], a.theta[i], a.eps_gamma, a.eps_n, ws, snap, acc);
+                        // hand the total in (the slot of this accumulator's last chunk: nobody else reads it), count out
+                        double done = 0.0;
+                        if (w.lane == 0) {
+                            snap[kSnapContrib + acc] = total;
+                            if (a.counters)
+                                atomicAdd(&a.counters[i], w.n_apply_lanes);
+                            if (a.status && w.status)
+                                atomicOr(&a.status[i], (int)w.status);
+                            __threadfence();
+                            done = atomicAdd(&snap[kSnapDone], 1.0) + 1.0;
+                        }
+                        done = __shfl_sync(0xffffffffu, done, 0);
+                        if (done != (double)__popc(active))
+                            continue; // another warp of this point is still at work
+                        __threadfence();
+                    } else if (acc != 0)
+                        continue; // (a record without a chain left: the first ticket writes the point out)
+                    double totals[kSymNA];
+#pragma unroll
+                    for (int c = 0; c < kSymNA; c++) {
+                        const volatile double *vs = snap;
+                        totals[c] = ((active >> c) & 1u) ? vs[kSnapContrib + c] : vs[kSnapDisc + c] + vs[kSnapTail + c];
+                    }
+                    symphony_tail_combine(a.theta[i], totals, out6, lobes4);
+                    w.n_apply_lanes = 0; // counted above
+                    w.status = 0;
                     resumed = true;
-                }
+                } else if (acc != 0)
+                    continue; // a point that starts over (s < 10) is one chain: the first ticket takes all of it
             }
         }
         if (!resumed)
@@ -93,8 +132,12 @@ __global__ void __launch_bounds__(kThreadsPerBlock, FUSED ? 3 : 4) k_symphony(Ba
                 for (int c = 0; c < 4; c++)
                     a.lobes4[(long long)c * a.n + i] = lobes4[c];
             }
-            if (a.counters)
-                a.counters[i] = w.n_apply_lanes + (a.from_reroute_list ? a.counters[i] : 0u);
+            if (a.counters) {
+                if (a.from_reroute_list)
+                    atomicAdd(&a.counters[i], w.n_apply_lanes); // on top of what the product kernel counted
+                else
+                    a.counters[i] = w.n_apply_lanes;
+            }
             const unsigned st = w.status | (any_nan ? kStatusNaN : 0u);
             if (a.status && st)
                 atomicOr(&a.status[i], (int)st);

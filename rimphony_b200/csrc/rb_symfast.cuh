@@ -67,7 +67,8 @@ constexpr double kNarrowPanel = 0.75; // outer panels narrower than this in u us
 // Layout of a hand-over record (doubles): the state of the chunk loop at the first chunk that
 // starts beyond kHandoverN, for the faithful continuation (rb_symphony.cuh symphony_tail_faithful).
 constexpr int kSnapNStart = 0, kSnapDeltaN = 1, kSnapIncr = 2, kSnapValid = 3, kSnapDisc = 4, kSnapTail = 12,
-              kSnapContrib = 20, kSnapActive = 28, kSnapDoubles = 32;
+              kSnapContrib = 20, kSnapActive = 28, kSnapDone = 29, kSnapDoubles = 32;
+// (kSnapDone: where the warps that finish the accumulators of a handed point count themselves out, k_symphony)
 
 constexpr int kSymInnerChan = 6;
 struct SymFastWS {
@@ -711,7 +712,10 @@ RB_FN void symphony_point_fast(Warp &w, const Dist &dist, double s, double theta
 #ifdef RB_DEVICE_BUILD
     if (w.lane == 0)
 #endif
+    {
         ws.snap[kSnapValid] = 0.0;
+        ws.snap[kSnapDone] = 0.0;
+    }
 
     for (int chunk_no = 0; chunk_no < kMaxChunks; chunk_no++) {
         if (!have_snap && n_lo_chunk >= kHandoverN && s >= 10.0 && s < 1e6) {
@@ -726,6 +730,7 @@ RB_FN void symphony_point_fast(Warp &w, const Dist &dist, double s, double theta
                 ws.snap[kSnapIncr] = incr_step_factor;
                 ws.snap[kSnapValid] = 1.0;
                 ws.snap[kSnapActive] = 0.0;
+                ws.snap[kSnapDone] = 0.0;
             }
             warp_fence();
 #ifdef RB_DEVICE_BUILD

@@ -358,9 +358,9 @@ RB_FN void symphony_point(Warp &w, const Dist &dist, double s, double theta, dou
 // accumulator that was still being integrated resumes the reference's own loop
 // (symphony.rs:225-292) from there, on its own, with the reference's rule sequence.
 template <int KIND, int GAMMA_CAP, int N_CAP>
-RB_FN void symphony_tail_faithful(Warp &w, const Dist &dist, double s, double theta, double epsrel_gamma,
-                                  double epsrel_n, SymWorkspace<false, GAMMA_CAP, N_CAP> &ws, const double *snap,
-                                  double (&out6)[6], double (&lobes4)[4])
+RB_FN double symphony_tail_faithful_one(Warp &w, const Dist &dist, double s, double theta, double epsrel_gamma,
+                                        double epsrel_n, SymWorkspace<false, GAMMA_CAP, N_CAP> &ws, const double *snap,
+                                        int c)
 {
     SymGeometry geom;
     geom.s = s;
@@ -373,26 +373,23 @@ RB_FN void symphony_tail_faithful(Warp &w, const Dist &dist, double s, double th
     nlist.bind(ws.n_store, N_CAP);
     SymGammaIntegral<KIND, false> G{&dist, &geom, &ws.orders, &glist, 1u, 0, epsrel_gamma};
 
-    const unsigned active = (unsigned)snap[28];
-    double total[kSymNA];
-    for (int c = 0; c < kSymNA; c++) {
-        const double disc = snap[4 + c];
-        if ((active >> c) & 1u) {
-            SymChunkState st{snap[0], snap[1], snap[2], snap[12 + c], snap[20 + c]};
-            G.sel = c;
-            G.want = 1u;
-            double ans[1];
-            sym_n_integration<KIND, false>(w, G, st.n_start, 1u, epsrel_n, nlist, ans, &st);
-            const double v = disc + ans[0];
-            total[c] = (v - v == 0.0) ? v : NAN;
-        } else {
-            total[c] = disc + snap[12 + c];
-        }
-    }
+    const double disc = snap[4 + c];
+    SymChunkState st{snap[0], snap[1], snap[2], snap[12 + c], snap[20 + c]};
+    G.sel = c;
+    G.want = 1u;
+    double ans[1];
+    sym_n_integration<KIND, false>(w, G, st.n_start, 1u, epsrel_n, nlist, ans, &st);
+    const double v = disc + ans[0];
+    return (v - v == 0.0) ? v : NAN;
+}
 
+// The eight accumulator totals -> the six coefficients and the four Stokes V lobes (symphony.rs:173-183)
+RB_FN void symphony_tail_combine(double theta, const double (&total)[kSymNA], double (&out6)[6], double (&lobes4)[4])
+{
+    const double cos_th = cos(theta);
     const double two_pi_e = kTwoPi * kElectronCharge;
-    const double pre_j = two_pi_e * two_pi_e / (kSpeedLight * fabs(geom.cos_th));
-    const double pre_a = -1.0 * two_pi_e * two_pi_e / (2.0 * kMassElectron * kSpeedLight * fabs(geom.cos_th));
+    const double pre_j = two_pi_e * two_pi_e / (kSpeedLight * fabs(cos_th));
+    const double pre_a = -1.0 * two_pi_e * two_pi_e / (2.0 * kMassElectron * kSpeedLight * fabs(cos_th));
     out6[0] = total[0] * pre_j;
     out6[1] = total[1] * pre_a;
     out6[2] = total[2] * pre_j;
@@ -403,6 +400,25 @@ RB_FN void symphony_tail_faithful(Warp &w, const Dist &dist, double s, double th
     lobes4[3] = total[7] * pre_a;
     out6[4] = lobes4[0] + lobes4[1];
     out6[5] = lobes4[2] + lobes4[3];
+}
+
+// All accumulators of a handed point one after the other (the host harness; the kernel gives each accumulator
+// its own warp, k_symphony in rb_kernels.cuh).
+template <int KIND, int GAMMA_CAP, int N_CAP>
+RB_FN void symphony_tail_faithful(Warp &w, const Dist &dist, double s, double theta, double epsrel_gamma,
+                                  double epsrel_n, SymWorkspace<false, GAMMA_CAP, N_CAP> &ws, const double *snap,
+                                  double (&out6)[6], double (&lobes4)[4])
+{
+    const unsigned active = (unsigned)snap[28];
+    double total[kSymNA];
+    for (int c = 0; c < kSymNA; c++) {
+        if ((active >> c) & 1u)
+            total[c] = symphony_tail_faithful_one<KIND, GAMMA_CAP, N_CAP>(w, dist, s, theta, epsrel_gamma, epsrel_n, ws,
+                                                                          snap, c);
+        else
+            total[c] = snap[4 + c] + snap[12 + c];
+    }
+    symphony_tail_combine(theta, total, out6, lobes4);
 }
 
 // ---------------------------------------------------------------------------
