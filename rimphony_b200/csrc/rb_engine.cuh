@@ -435,8 +435,12 @@ struct OuterLevel {
 RB_FN void acc_clear(const Warp &w, OuterAcc &acc)
 {
 #ifdef RB_DEVICE_BUILD
-    if (w.lane < 3 * kEngChan)
-        acc.k[w.lane] = 0.0; // k, d, a are contiguous
+    if (w.lane < kEngChan)
+        acc.k[w.lane] = 0.0;
+    else if (w.lane < 2 * kEngChan)
+        acc.d[w.lane - kEngChan] = 0.0;
+    else if (w.lane < 3 * kEngChan)
+        acc.a[w.lane - 2 * kEngChan] = 0.0;
 #else
     (void)w;
     for (int i = 0; i < kEngChan; i++)
