@@ -66,7 +66,7 @@ struct BatchArgs {
     unsigned long long *class_counts; // [2 kernels][kCostClasses]
 };
 
-constexpr int kCostClasses = 3;
+constexpr int kCostClasses = 4;
 
 // One diagnostic of the Symphony double integral at `count` arguments of ONE point (the
 // point is element 0 of the BatchArgs arrays): lib.rs:254-298.

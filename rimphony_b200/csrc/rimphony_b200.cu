@@ -62,9 +62,15 @@ __global__ void k_classify(rbhost::BatchArgs a)
     const double s = a.s[i];
     const double sigma0 = s * sin(a.theta[i]);
     const int cs = (s >= 300.0) ? 0 : ((s >= 10.0) ? 1 : 2);
-    int ch = (s < 1.0) ? 0 : ((sigma0 < 3.0) ? 1 : 2); // NaN lands in the last class
+    int ch = (s < 1.0) ? 1 : ((sigma0 < 3.0) ? 2 : 3); // NaN lands in the last class
+    // The points that can run into the application budget (20 k applications, 15 x the mean; measured on 65 536
+    // points: all but a handful of those above 15 k have s sin(theta) < 0.1 and s < 10) start first: a launch is at
+    // least as long as its longest point, and one of these picked up late is the tail of a 1e5-point launch
+    // (simulated on the measured costs: 1.29 -> 1.05 x the ideal makespan at 131 072 points).
+    if (sigma0 < 0.1 && s < 10.0)
+        ch = 0;
     if (a.hey_free_below > 0.0 && s < a.hey_free_below)
-        ch = 2;
+        ch = 3;
     const unsigned long long ks = atomicAdd(&a.class_counts[cs], 1ULL);
     a.order[(size_t)cs * a.n + ks] = (int)i;
     const unsigned long long kh = atomicAdd(&a.class_counts[rbhost::kCostClasses + ch], 1ULL);
