@@ -152,7 +152,7 @@ inline double rb_rsqrt_seed(double x)
 #endif
 RB_FN double rb_sqrt(double x)
 {
-#ifdef RB_NO_LEAN_SQRT
+#ifdef RB_NO_LEAN_SQRT // tuning knob of the A/B in profiles/r02_instruction_work_ab.log (s15): the IEEE sequence
     return sqrt(x);
 #endif
     const double y = rb_rsqrt_seed(x);
